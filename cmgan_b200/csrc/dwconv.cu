@@ -1,0 +1,138 @@
+// GLU + depthwise Conv1d(k = 31, zero pad 15/15, bias) of the conformer convolution module.
+// Reference: conformer.py:30-48,164-168.  Input g (M, 256) = pointwise-conv output, u = g[:, :128] * sigmoid(g[:, 128:]),
+// out[tok, c] = bias[c] + sum_k w[c, k] * u[tok + k - 15, c] along the sequence axis (strided rows, SeqGeom).
+// HBM-bound: one pass over g, one write of out; the 31-tap window lives in shared memory.
+#include "common.cuh"
+#include "../../include/cmgan_b200.h"
+
+namespace {
+
+constexpr int CH = 128, KS = 31, PADL = 15, TT = 32, ROWS = TT + KS - 1;   // 62 staged rows per tile
+
+__device__ __forceinline__ void stage_glu(float* U, const float* __restrict__ g, long base, long tok_stride, int t0, int L) {
+    // U[r][c], r in [0, ROWS): token t0 - 15 + r
+    for (int idx = threadIdx.x; idx < ROWS * CH; idx += blockDim.x) {
+        int r = idx / CH, c = idx % CH;
+        int tok = t0 - PADL + r;
+        float u = 0.f;
+        if (tok >= 0 && tok < L) {
+            const float* p = g + (base + (long)tok * tok_stride) * (2 * CH);
+            u = __ldg(p + c) * sigmoidf_(__ldg(p + CH + c));
+        }
+        U[idx] = u;
+    }
+}
+
+__global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __restrict__ g, SeqGeom sg, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out) {
+    __shared__ float U[ROWS * CH];
+    const int s = blockIdx.x, t0 = blockIdx.y * TT;
+    const long base = seq_base(sg, s);
+    stage_glu(U, g, base, sg.tok_stride, t0, sg.L);
+    const int c = threadIdx.x % CH, half = threadIdx.x / CH;     // 2 halves x 16 tokens
+    float wr[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) wr[k] = __ldg(w + c * KS + k);
+    const float b = __ldg(bias + c);
+    __syncthreads();
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+        const int tl = half * 16 + grp * 4;
+        float a0 = b, a1 = b, a2 = b, a3 = b;
+#pragma unroll
+        for (int m = 0; m < KS + 3; ++m) {
+            float u = U[(tl + m) * CH + c];
+            if (m < KS) a0 = fmaf(wr[m], u, a0);
+            if (m >= 1 && m - 1 < KS) a1 = fmaf(wr[m - 1], u, a1);
+            if (m >= 2 && m - 2 < KS) a2 = fmaf(wr[m - 2], u, a2);
+            if (m >= 3) a3 = fmaf(wr[m - 3], u, a3);
+        }
+        float a[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int tok = t0 + tl + q;
+            if (tok < sg.L) out[(base + (long)tok * sg.tok_stride) * CH + c] = a[q];
+        }
+    }
+}
+
+// backward.  dz = grad wrt out (M, 128).  dg (M, 256) overwritten; dw (128, 31), dbias (128) accumulated.
+__global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ dz, SeqGeom sg,
+                                                             const float* __restrict__ w, int seqs_per_block, float* __restrict__ dg,
+                                                             float* __restrict__ dw, float* __restrict__ dbias) {
+    extern __shared__ float smem[];
+    float* U = smem;                 // [ROWS][CH]
+    float* DZ = smem + ROWS * CH;    // [ROWS][CH]
+    const int c = threadIdx.x % CH, half = threadIdx.x / CH;
+    float wr[KS], dwr[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { wr[k] = __ldg(w + c * KS + k); dwr[k] = 0.f; }
+    float db = 0.f;
+    const int s_beg = blockIdx.x * seqs_per_block, s_end = min(s_beg + seqs_per_block, sg.n_seq);
+    for (int s = s_beg; s < s_end; ++s) {
+        const long base = seq_base(sg, s);
+        for (int t0 = 0; t0 < sg.L; t0 += TT) {
+            __syncthreads();
+            stage_glu(U, g, base, sg.tok_stride, t0, sg.L);
+            for (int idx = threadIdx.x; idx < ROWS * CH; idx += blockDim.x) {
+                int r = idx / CH, cc = idx % CH;
+                int tok = t0 - PADL + r;
+                DZ[idx] = (tok >= 0 && tok < sg.L) ? __ldg(dz + (base + (long)tok * sg.tok_stride) * CH + cc) : 0.f;
+            }
+            __syncthreads();
+            for (int tl = half * 16; tl < half * 16 + 16; ++tl) {
+                const int tok = t0 + tl;
+                if (tok >= sg.L) break;
+                // du[tok] = sum_k w[k] * dz[tok - k + 15]  ->  local rows tl + 30 - k
+                float du = 0.f;
+#pragma unroll
+                for (int k = 0; k < KS; ++k) du = fmaf(wr[k], DZ[(tl + 30 - k) * CH + c], du);
+                // dw[k] += dz[tok] * u[tok + k - 15] -> local rows tl + k
+                const float dzc = DZ[(tl + PADL) * CH + c];
+#pragma unroll
+                for (int k = 0; k < KS; ++k) dwr[k] = fmaf(dzc, U[(tl + k) * CH + c], dwr[k]);
+                db += dzc;
+                const long row = base + (long)tok * sg.tok_stride;
+                const float a = __ldg(g + row * (2 * CH) + c);
+                const float sg_ = sigmoidf_(__ldg(g + row * (2 * CH) + CH + c));
+                dg[row * (2 * CH) + c] = du * sg_;
+                dg[row * (2 * CH) + CH + c] = du * a * sg_ * (1.f - sg_);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) atomicAdd(dw + c * KS + k, dwr[k]);
+    atomicAdd(dbias + c, db);
+}
+
+}  // namespace
+
+CMGAN_API int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* bias, int B, int T, int F, int axis, float* out, void* stream) {
+    CMGAN_REQUIRE(g && w && bias && out, "cmgan_glu_dwconv_fwd: null pointer");
+    CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_glu_dwconv_fwd: bad axis");
+    SeqGeom sg = make_seq_geom(B, T, F, axis);
+    if (sg.n_seq == 0) return 0;
+    dim3 grid(sg.n_seq, cdiv(sg.L, TT));
+    glu_dwconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, sg, w, bias, out);
+    return cmgan_check_launch("glu_dwconv_fwd_kernel");
+}
+
+CMGAN_API int cmgan_glu_dwconv_bwd(const float* g, const float* dz, const float* w, int B, int T, int F, int axis, float* dg, float* dw,
+                                   float* dbias, void* stream) {
+    CMGAN_REQUIRE(g && dz && w && dg && dw && dbias, "cmgan_glu_dwconv_bwd: null pointer");
+    CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_glu_dwconv_bwd: bad axis");
+    SeqGeom sg = make_seq_geom(B, T, F, axis);
+    if (sg.n_seq == 0) return 0;
+    static bool attr_set = false;
+    const int smem = 2 * ROWS * CH * (int)sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(glu_dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        CMGAN_REQUIRE(e == cudaSuccess, "cmgan_glu_dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    // enough blocks for ~4 waves of 148 SMs x 3 resident blocks, but at least one sequence per block
+    int spb = sg.n_seq / (148 * 3 * 4);
+    if (spb < 1) spb = 1;
+    glu_dwconv_bwd_kernel<<<cdiv(sg.n_seq, spb), 256, smem, (cudaStream_t)stream>>>(g, dz, sg, w, spb, dg, dw, dbias);
+    return cmgan_check_launch("glu_dwconv_bwd_kernel");
+}

@@ -1,0 +1,289 @@
+// fp32 FFMA GEMMs with fused gather (implicit convolution), A-operand prologues and epilogues.
+// These are the exact-fp32 baseline for every dense contraction of the path (see gemm_args.h for the
+// contract); the tf32 tcgen05 kernels in gemm_tc.cu implement the same contract for the hot shapes.
+#include "common.cuh"
+#include "../../include/cmgan_b200.h"
+#include "gemm_args.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr int AS_LD = BM + 4;
+
+struct RowInfo { int b, y, x; bool ok; };
+
+__device__ __forceinline__ RowInfo decode_row(const CmganGemmArgs& g, int m) {
+    RowInfo r;
+    r.ok = m < g.M;
+    if (g.conv) {
+        int x = m % g.OW; int t = m / g.OW;
+        r.x = x; r.y = t % g.OH; r.b = t / g.OH;
+    } else { r.b = 0; r.y = 0; r.x = m; }
+    return r;
+}
+
+// in_row for (row, tap) or -1 when the tap falls into padding / a stride hole
+__device__ __forceinline__ long in_row_of(const CmganGemmArgs& g, const RowInfo& r, int tap) {
+    if (!r.ok) return -1;
+    if (!g.conv) return r.x;
+    int iy = r.y * g.mul_y + g.dy[tap];
+    int ix = r.x * g.mul_x + g.dx[tap];
+    if (iy < 0 || ix < 0) return -1;
+    if (g.div_y > 1) { if (iy % g.div_y) return -1; iy /= g.div_y; }
+    if (g.div_x > 1) { if (ix % g.div_x) return -1; ix /= g.div_x; }
+    if (iy >= g.IH || ix >= g.IW) return -1;
+    return ((long)r.b * g.IH + iy) * g.IW + ix;
+}
+
+__device__ __forceinline__ float apply_pro(const CmganGemmArgs& g, float a, long r, int k, float mean, float rstd) {
+    switch (g.pro) {
+        case CMGAN_PRO_LN: return (a - mean) * rstd * __ldg(g.p1 + k) + __ldg(g.p2 + k);
+        case CMGAN_PRO_SWISH_DROP: return swishf_(a) * cmgan_drop_scale(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
+        case CMGAN_PRO_BN_SWISH: return swishf_(a * __ldg(g.p0 + k) + __ldg(g.p1 + k));
+        case CMGAN_PRO_DROP: return a * g.pro_alpha * cmgan_drop_scale(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
+        case CMGAN_PRO_IN_PRELU: {
+            long b = r / g.rows_per_batch;
+            float z = a * __ldg(g.p0 + b * g.pstride + k) + __ldg(g.p1 + b * g.pstride + k);
+            return z >= 0.f ? z : z * __ldg(g.p2 + k);
+        }
+        default: return a;
+    }
+}
+
+// loads 4 consecutive k of one A row (prologue applied); zeros where masked
+template <int VEC>
+__device__ __forceinline__ void load_a4(const CmganGemmArgs& g, long r, int tap, int k, float out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0.f;
+    if (r < 0 || k >= g.Cin) return;
+    const float* p = g.A + g.tap_off[tap] + r * g.lda + k;
+    float mean = 0.f, rstd = 0.f;
+    if (g.pro == CMGAN_PRO_LN) { float2 st = __ldg(reinterpret_cast<const float2*>(g.p0) + r); mean = st.x; rstd = st.y; }
+    if (VEC == 4 && k + 3 < g.Cin) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        if (g.pro != CMGAN_PRO_NONE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[i] = apply_pro(g, out[i], r, k + i, mean, rstd);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (k + i < g.Cin) out[i] = apply_pro(g, __ldg(p + i), r, k + i, mean, rstd);
+    }
+}
+
+__device__ __forceinline__ float epilogue(const CmganGemmArgs& g, float v, long m, int n, const float* cptr) {
+    switch (g.epi) {
+        case CMGAN_EPI_DROP_RES: {
+            float o = g.alpha * v * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+            if (g.R) o += __ldg(g.R + m * g.ldr + n);
+            return o;
+        }
+        case CMGAN_EPI_DSWISH_DROP: {
+            float h = __ldg(g.aux + m * g.ldaux + n);
+            return v * dswishf_(h) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+        }
+        case CMGAN_EPI_DBNSWISH: {
+            float z = __ldg(g.aux + m * g.ldaux + n) * __ldg(g.e0 + n) + __ldg(g.e1 + n);
+            return v * dswishf_(z);
+        }
+        case CMGAN_EPI_ACC: return g.alpha * v + *cptr;
+        default: return v;
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(NT, 2) gemm_rows_kernel(const __grid_constant__ CmganGemmArgs g) {
+    __shared__ __align__(16) float As[BK][AS_LD];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int ty = tid >> 4, tx = tid & 15;           // compute mapping: rows ty*8.., cols tx*4..
+    const int lr = tid >> 2, lk = (tid & 3) * 4;        // A load mapping: rows lr, lr+64; k offset lk
+    const int bk = tid >> 4, bn = (tid & 15) * 4;       // B load mapping
+    const RowInfo ri0 = decode_row(g, m0 + lr), ri1 = decode_row(g, m0 + lr + 64);
+    const int cpt = (g.Cin + BK - 1) / BK;              // chunks per tap
+    const int nchunks = cpt * g.ntaps;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float ra0[4], ra1[4], rb[4];
+    auto fetch = [&](int c) {
+        int tap = c / cpt, k0 = (c - tap * cpt) * BK;
+        load_a4<VEC>(g, in_row_of(g, ri0, tap), tap, k0 + lk, ra0);
+        load_a4<VEC>(g, in_row_of(g, ri1, tap), tap, k0 + lk, ra1);
+        int kk = k0 + bk;
+        const float* bp = g.B + (long)tap * g.sb_tap + (long)kk * g.sb_k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + bn + j;
+            rb[j] = (kk < g.Cin && n < g.N) ? __ldg(bp + (long)n * g.sb_n) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { As[lk + i][lr] = ra0[i]; As[lk + i][lr + 64] = ra1[i]; }
+        *reinterpret_cast<float4*>(&Bs[bk][bn]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+        __syncthreads();
+        if (c + 1 < nchunks) fetch(c + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long m = m0 + ty * 8 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j] + (g.bias ? __ldg(g.bias + n) : 0.f);
+            float* cp = g.C + m * g.ldc + n;
+            *cp = epilogue(g, v, m, n, cp);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient:  dW(tap, k, n) += sum_m pro(A[in_row(m,tap), k]) * prod(D[m, n]);  dbias[n] += sum_m prod(D[m,n])
+constexpr int WK = 64, WN = 64, WR = 16, MCH = 1024;
+
+template <int VEC>
+__global__ void __launch_bounds__(NT, 2) gemm_wgrad_kernel(const __grid_constant__ CmganGemmArgs g) {
+    __shared__ __align__(16) float As[WR][WK];
+    __shared__ __align__(16) float Ds[WR][WN];
+    const int tid = threadIdx.x;
+    const int ktiles = (g.Cin + WK - 1) / WK;
+    const int tap = blockIdx.x / ktiles, k0 = (blockIdx.x % ktiles) * WK;
+    const int n0 = blockIdx.y * WN;
+    const long mbeg = (long)blockIdx.z * MCH;
+    const long mend = mbeg + MCH < g.M ? mbeg + MCH : g.M;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    const bool do_bias = g.dbias != nullptr && blockIdx.x == 0;
+
+    float ra[4], rd[4];
+    auto fetch = [&](long mb) {
+        long m = mb + lr;
+        RowInfo ri = decode_row(g, (int)(m < mend ? m : g.M));   // m >= mend -> masked (ri.ok false)
+        if (m >= mend) ri.ok = false;
+        load_a4<VEC>(g, in_row_of(g, ri, tap), tap, k0 + lc, ra);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + lc + j;
+            float d = 0.f;
+            if (m < mend && n < g.N) {
+                d = __ldg(g.D + m * g.ldd + n);
+                if (g.prod == 1) d *= g.alpha * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+            }
+            rd[j] = d;
+        }
+    };
+    if (mbeg < mend) fetch(mbeg);
+    for (long mb = mbeg; mb < mend; mb += WR) {
+        *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+        *reinterpret_cast<float4*>(&Ds[lr][lc]) = make_float4(rd[0], rd[1], rd[2], rd[3]);
+        __syncthreads();
+        if (mb + WR < mend) fetch(mb + WR);
+#pragma unroll
+        for (int r = 0; r < WR; ++r) {
+            float4 a = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
+            float4 d = *reinterpret_cast<const float4*>(&Ds[r][tx * 4]);
+            float aa[4] = {a.x, a.y, a.z, a.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], dd[j], acc[i][j]);
+        }
+        if (do_bias && tid < WN) {
+#pragma unroll
+            for (int r = 0; r < WR; ++r) bsum += Ds[r][tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int k = k0 + ty * 4 + i;
+        if (k >= g.Cin) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            atomicAdd(g.C + (long)tap * g.sb_tap + (long)k * g.sb_k + (long)n * g.sb_n, acc[i][j]);
+        }
+    }
+    if (do_bias && tid < WN && n0 + tid < g.N) atomicAdd(g.dbias + n0 + tid, bsum);
+}
+
+bool vec_ok(const CmganGemmArgs& a) {
+    if (a.lda % 4 || a.Cin % 4 || ((uintptr_t)a.A & 15)) return false;
+    for (int t = 0; t < a.ntaps; ++t)
+        if (a.tap_off[t] % 4) return false;
+    return true;
+}
+
+int validate(const CmganGemmArgs* a, const char* who) {
+    CMGAN_REQUIRE(a != nullptr, "%s: null args", who);
+    CMGAN_REQUIRE(a->M >= 0 && a->N > 0 && a->Cin > 0, "%s: bad shape M=%d N=%d Cin=%d", who, a->M, a->N, a->Cin);
+    CMGAN_REQUIRE(a->ntaps >= 1 && a->ntaps <= CMGAN_MAX_TAPS, "%s: ntaps=%d out of range", who, a->ntaps);
+    CMGAN_REQUIRE(a->A && a->C, "%s: null A/C pointer", who);
+    if (a->conv) {
+        CMGAN_REQUIRE(a->OH > 0 && a->OW > 0 && a->IH > 0 && a->IW > 0, "%s: bad conv geometry", who);
+        CMGAN_REQUIRE(a->mul_y >= 1 && a->mul_x >= 1 && a->div_y >= 1 && a->div_x >= 1, "%s: bad stride", who);
+        CMGAN_REQUIRE((long)a->M % ((long)a->OH * a->OW) == 0, "%s: M=%d is not a multiple of OH*OW", who, a->M);
+    }
+    if (a->pro == CMGAN_PRO_LN) CMGAN_REQUIRE(a->p0 && a->p1 && a->p2, "%s: LN prologue needs stats/gamma/beta", who);
+    if (a->pro == CMGAN_PRO_BN_SWISH) CMGAN_REQUIRE(a->p0 && a->p1, "%s: BN prologue needs scale/shift", who);
+    if (a->pro == CMGAN_PRO_IN_PRELU) CMGAN_REQUIRE(a->p0 && a->p1 && a->p2 && a->rows_per_batch > 0, "%s: IN prologue params", who);
+    return 0;
+}
+
+}  // namespace
+
+// C[M, N] = epi(bias + sum_taps pro(A) * B); see gemm_args.h.  Replaces every nn.Linear / nn.Conv1d(k=1) /
+// nn.Conv2d of reference generator.py:24-32,53-63,108 and conformer.py:82-84,140-144,163,173 and their
+// autograd data gradients.
+CMGAN_API int cmgan_gemm_rows_f32(const CmganGemmArgs* a, void* stream) {
+    if (validate(a, "cmgan_gemm_rows_f32")) return -1;
+    CMGAN_REQUIRE(a->B != nullptr, "cmgan_gemm_rows_f32: null B");
+    if (a->M == 0) return 0;
+    if (a->epi == CMGAN_EPI_DSWISH_DROP || a->epi == CMGAN_EPI_DBNSWISH) CMGAN_REQUIRE(a->aux != nullptr, "gemm_rows: epilogue needs aux");
+    dim3 grid(cdiv(a->M, BM), cdiv(a->N, BN));
+    if (vec_ok(*a)) gemm_rows_kernel<4><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
+    else gemm_rows_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
+    return cmgan_check_launch("gemm_rows_kernel");
+}
+
+// dW += A^T D (accumulates with atomics into a[C], laid out like B in the forward call) and dbias += colsum(D).
+CMGAN_API int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream) {
+    if (validate(a, "cmgan_gemm_wgrad_f32")) return -1;
+    CMGAN_REQUIRE(a->D != nullptr, "cmgan_gemm_wgrad_f32: null D");
+    if (a->M == 0) return 0;
+    dim3 grid(cdiv(a->Cin, WK) * a->ntaps, cdiv(a->N, WN), cdiv(a->M, MCH));
+    if (vec_ok(*a)) gemm_wgrad_kernel<4><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
+    else gemm_wgrad_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
+    return cmgan_check_launch("gemm_wgrad_kernel");
+}

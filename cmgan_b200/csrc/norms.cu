@@ -1,0 +1,360 @@
+// LayerNorm / InstanceNorm / BatchNorm statistics, applies and gradients (HBM-bound row kernels).
+// Channel-last rows; LayerNorm is over the 64 channels of one row (one warp per row, shuffle reductions);
+// Instance/BatchNorm statistics are per (group, channel) over all rows of a group (group = batch element
+// for InstanceNorm2d, a single group for BatchNorm1d), accumulated in double.
+#include "common.cuh"
+#include "../../include/cmgan_b200.h"
+
+namespace {
+
+constexpr int LN_C = 64;
+constexpr float EPS = 1e-5f;
+
+// ---------------------------------------------------------------- LayerNorm (ref: conformer.py:68,161,214)
+// stats[m] = (mean, rstd)
+__global__ void ln_stats_kernel(const float* __restrict__ x, long ldx, long M, float2* __restrict__ stats) {
+    long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float2 v = __ldg(reinterpret_cast<const float2*>(x + row * ldx) + lane);
+    float mean = warp_sum(v.x + v.y) * (1.0f / LN_C);
+    float d0 = v.x - mean, d1 = v.y - mean;
+    float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / LN_C);
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + EPS));
+}
+
+// y = LN(x) * gamma + beta (+ res);  stats written for the backward pass
+__global__ void ln_apply_kernel(const float* __restrict__ x, long ldx, long M, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ res, long ldr,
+                                float* __restrict__ y, long ldy, float2* __restrict__ stats) {
+    long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float2 v = __ldg(reinterpret_cast<const float2*>(x + row * ldx) + lane);
+    float mean = warp_sum(v.x + v.y) * (1.0f / LN_C);
+    float d0 = v.x - mean, d1 = v.y - mean;
+    float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / LN_C);
+    float rstd = rsqrtf(var + EPS);
+    float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + lane);
+    float2 b = __ldg(reinterpret_cast<const float2*>(beta) + lane);
+    float2 o = make_float2(d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y);
+    if (res) { float2 r = __ldg(reinterpret_cast<const float2*>(res + row * ldr) + lane); o.x += r.x; o.y += r.y; }
+    reinterpret_cast<float2*>(y + row * ldy)[lane] = o;
+    if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+// dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)) (+ res);  dgamma += sum dy*xhat;  dbeta += sum dy
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
+                              const float2* __restrict__ stats, const float* __restrict__ gamma, long M,
+                              const float* __restrict__ res, long ldr, const float* __restrict__ res2, long ldr2,
+                              float* __restrict__ dx, long lddx,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp) {
+    __shared__ float sg[8][LN_C], sb[8][LN_C];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    long r0 = ((long)blockIdx.x * nw + warp) * rows_per_warp;
+    float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + lane);
+    float2 ag = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
+    for (int i = 0; i < rows_per_warp; ++i) {
+        long row = r0 + i;
+        if (row >= M) break;
+        float2 v = __ldg(reinterpret_cast<const float2*>(x + row * ldx) + lane);
+        float2 d = __ldg(reinterpret_cast<const float2*>(dy + row * lddy) + lane);
+        float2 st = __ldg(stats + row);
+        float xh0 = (v.x - st.x) * st.y, xh1 = (v.y - st.x) * st.y;
+        float dg0 = d.x * g.x, dg1 = d.y * g.y;
+        float m1 = warp_sum(dg0 + dg1) * (1.0f / LN_C);
+        float m2 = warp_sum(dg0 * xh0 + dg1 * xh1) * (1.0f / LN_C);
+        float2 o = make_float2(st.y * (dg0 - m1 - xh0 * m2), st.y * (dg1 - m1 - xh1 * m2));
+        if (res) { float2 r = __ldg(reinterpret_cast<const float2*>(res + row * ldr) + lane); o.x += r.x; o.y += r.y; }
+        if (res2) { float2 r = __ldg(reinterpret_cast<const float2*>(res2 + row * ldr2) + lane); o.x += r.x; o.y += r.y; }
+        reinterpret_cast<float2*>(dx + row * lddx)[lane] = o;
+        ag.x += d.x * xh0; ag.y += d.y * xh1; ab.x += d.x; ab.y += d.y;
+    }
+    sg[warp][2 * lane] = ag.x; sg[warp][2 * lane + 1] = ag.y;
+    sb[warp][2 * lane] = ab.x; sb[warp][2 * lane + 1] = ab.y;
+    __syncthreads();
+    if (threadIdx.x < LN_C) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < nw; ++w) { a += sg[w][threadIdx.x]; b += sb[w][threadIdx.x]; }
+        atomicAdd(dgamma + threadIdx.x, a);
+        atomicAdd(dbeta + threadIdx.x, b);
+    }
+}
+
+// ---------------------------------------------------------------- group statistics (InstanceNorm2d / BatchNorm1d)
+// sums[(grp*C + c)*2 + {0,1}] += sum x, sum x^2 over the rows of group grp.  Block = one chunk of rows of
+// one group; thread = (row-subgroup, channel).
+__global__ void norm_stats_kernel(const float* __restrict__ x, long ldx, long rows_per_group, int C, int chunk,
+                                  double* __restrict__ sums) {
+    extern __shared__ double sm[];
+    int grp = blockIdx.y;
+    long r_beg = (long)blockIdx.x * chunk;
+    long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
+    int c = threadIdx.x % C, rg = threadIdx.x / C, nrg = blockDim.x / C;
+    float s = 0.f, q = 0.f;
+    const float* base = x + ((long)grp * rows_per_group) * ldx + c;
+    if (rg < nrg)
+        for (long r = r_beg + rg; r < r_end; r += nrg) { float v = __ldg(base + r * ldx); s += v; q = fmaf(v, v, q); }
+    sm[threadIdx.x * 2] = s; sm[threadIdx.x * 2 + 1] = q;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double ds = 0.0, dq = 0.0;
+        for (int g = 0; g < nrg; ++g) { ds += sm[(g * C + c) * 2]; dq += sm[(g * C + c) * 2 + 1]; }
+        atomicAdd(sums + ((long)grp * C + c) * 2, ds);
+        atomicAdd(sums + ((long)grp * C + c) * 2 + 1, dq);
+    }
+}
+
+// mode 0: InstanceNorm / train-mode BatchNorm: statistics from sums (biased variance for the normalisation)
+// mode 1: eval-mode BatchNorm: running statistics
+// outputs per (grp, c): scale = gamma*rstd, shift = beta - mean*scale, mean, rstd (table stride = tstride)
+// when running_mean != null and mode 0: running <- (1-mom)*running + mom*(mean, unbiased var) (BatchNorm1d train)
+__global__ void norm_finalize_kernel(const double* __restrict__ sums, long n, int G, int C, int mode,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                     float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, long tstride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * C) return;
+    int grp = i / C, c = i % C;
+    float mean, var;
+    if (mode == 1) { mean = running_mean[c]; var = running_var[c]; }
+    else {
+        double m = sums[(long)i * 2] / (double)n;
+        double v = sums[(long)i * 2 + 1] / (double)n - m * m;
+        if (v < 0.0) v = 0.0;
+        mean = (float)m; var = (float)v;
+        if (running_mean) {
+            double unb = n > 1 ? v * (double)n / (double)(n - 1) : v;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    }
+    float rstd = rsqrtf(var + EPS);
+    float sc = gamma[c] * rstd;
+    long o = (long)grp * tstride + c;
+    scale[o] = sc; shift[o] = beta[c] - mean * sc;
+    if (mean_out) mean_out[o] = mean;
+    if (rstd_out) rstd_out[o] = rstd;
+}
+
+// backward pass 1.  z = x*scale + shift; act: 0 none, 1 PReLU(slope[c]);  g = dact * act'(z)
+//   S[(grp*C+c)*2 + {0,1}] += sum g, sum g*xhat   (xhat = (x - mean) * rstd);   dslope[c] += sum dact * z * [z<0]
+__global__ void norm_bwd_reduce_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dact, long ldd,
+                                       long rows_per_group, int C, int chunk, int act, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, long tstride, const float* __restrict__ slope,
+                                       double* __restrict__ S, float* __restrict__ dslope) {
+    extern __shared__ double sm[];
+    int grp = blockIdx.y;
+    long r_beg = (long)blockIdx.x * chunk;
+    long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
+    int c = threadIdx.x % C, rg = threadIdx.x / C, nrg = blockDim.x / C;
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (rg < nrg) {
+        long t = (long)grp * tstride + c;
+        float sc = scale[t], sh = shift[t], mu = mean[t], rs = rstd[t];
+        float a = act ? slope[c] : 1.f;
+        long rb = (long)grp * rows_per_group;
+        for (long r = r_beg + rg; r < r_end; r += nrg) {
+            float v = __ldg(x + (rb + r) * ldx + c);
+            float d = __ldg(dact + (rb + r) * ldd + c);
+            float z = v * sc + sh;
+            float gq = d;
+            if (act && z < 0.f) { gq = d * a; s3 = fmaf(d, z, s3); }
+            s1 += gq; s2 = fmaf(gq, (v - mu) * rs, s2);
+        }
+    }
+    sm[threadIdx.x * 3] = s1; sm[threadIdx.x * 3 + 1] = s2; sm[threadIdx.x * 3 + 2] = s3;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double a1 = 0, a2 = 0, a3 = 0;
+        for (int g = 0; g < nrg; ++g) { a1 += sm[(g * C + c) * 3]; a2 += sm[(g * C + c) * 3 + 1]; a3 += sm[(g * C + c) * 3 + 2]; }
+        atomicAdd(S + ((long)grp * C + c) * 2, a1);
+        atomicAdd(S + ((long)grp * C + c) * 2 + 1, a2);
+        if (act && dslope) atomicAdd(dslope + c, (float)a3);
+    }
+}
+
+// backward pass 2.  dx = scale * (g - [train] (S1/n + xhat*S2/n));  also dgamma[c] += S2, dbeta[c] += S1 (block 0 only)
+__global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dact, long ldd,
+                                      long rows_per_group, int G, int C, int act, int use_batch_stats,
+                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd, long tstride,
+                                      const float* __restrict__ slope, const double* __restrict__ S,
+                                      float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    long total = (long)G * rows_per_group * C;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (long)G * C && dgamma) {   // one thread per (grp, c): fold the per-group sums into the parameter grads
+        int c = (int)(i % C);
+        atomicAdd(dgamma + c, (float)S[i * 2 + 1]);
+        atomicAdd(dbeta + c, (float)S[i * 2]);
+    }
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long row = i / C;
+    int grp = (int)(row / rows_per_group);
+    long t = (long)grp * tstride + c;
+    float sc = scale[t], sh = shift[t], mu = mean[t], rs = rstd[t];
+    float v = __ldg(x + row * ldx + c), d = __ldg(dact + row * ldd + c);
+    float z = v * sc + sh;
+    float gq = (act && z < 0.f) ? d * slope[c] : d;
+    float o = gq;
+    if (use_batch_stats) {
+        double inv_n = 1.0 / (double)rows_per_group;
+        float m1 = (float)(S[((long)grp * C + c) * 2] * inv_n), m2 = (float)(S[((long)grp * C + c) * 2 + 1] * inv_n);
+        o = gq - m1 - (v - mu) * rs * m2;
+    }
+    dx[row * lddx + c] = sc * o;
+}
+
+// y[row, c] = act(x*scale+shift) materialised (used where the consumer is not a GEMM with a prologue)
+__global__ void norm_apply_kernel(const float* __restrict__ x, long ldx, long rows_per_group, int G, int C, int act,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, long tstride,
+                                  const float* __restrict__ slope, float* __restrict__ y, long ldy) {
+    long total = (long)G * rows_per_group * C;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long row = i / C;
+    long t = (row / rows_per_group) * tstride + c;
+    float z = __ldg(x + row * ldx + c) * scale[t] + shift[t];
+    if (act == 1 && z < 0.f) z *= slope[c];
+    else if (act == 2) z = swishf_(z);
+    y[row * ldy + c] = z;
+}
+
+__global__ void fill_kernel(float* p, long n, float v) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void copy_rows_kernel(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, long M, int C) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = M * (C / 4);
+    if (i >= total) return;
+    long row = i / (C / 4); int c4 = (int)(i % (C / 4));
+    reinterpret_cast<float4*>(dst + row * ldd)[c4] = __ldg(reinterpret_cast<const float4*>(src + row * lds) + c4);
+}
+
+__global__ void add_rows_kernel(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, long M, int C) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = M * (C / 4);
+    if (i >= total) return;
+    long row = i / (C / 4); int c4 = (int)(i % (C / 4));
+    float4 a = __ldg(reinterpret_cast<const float4*>(src + row * lds) + c4);
+    float4* d = reinterpret_cast<float4*>(dst + row * ldd) + c4;
+    float4 b = *d;
+    *d = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+}  // namespace
+
+CMGAN_API int cmgan_ln_stats(const float* x, long long ldx, long long M, float* stats, void* stream) {
+    CMGAN_REQUIRE(x && stats && ldx % 2 == 0, "cmgan_ln_stats: bad arguments");
+    if (M == 0) return 0;
+    ln_stats_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, M, reinterpret_cast<float2*>(stats));
+    return cmgan_check_launch("ln_stats_kernel");
+}
+
+// y = LayerNorm(x) * gamma + beta + res  (res, stats optional); reference conformer.py:214,222 + generator.py:95,97
+CMGAN_API int cmgan_ln_apply(const float* x, long long ldx, long long M, const float* gamma, const float* beta,
+                             const float* res, long long ldr, float* y, long long ldy, float* stats, void* stream) {
+    CMGAN_REQUIRE(x && y && gamma && beta && ldx % 2 == 0 && ldy % 2 == 0 && ldr % 2 == 0, "cmgan_ln_apply: bad arguments");
+    if (M == 0) return 0;
+    ln_apply_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, M, gamma, beta, res, ldr, y, ldy,
+                                                                 reinterpret_cast<float2*>(stats));
+    return cmgan_check_launch("ln_apply_kernel");
+}
+
+CMGAN_API int cmgan_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* stats,
+                           const float* gamma, long long M, const float* res, long long ldr, const float* res2, long long ldr2,
+                           float* dx, long long lddx, float* dgamma, float* dbeta, void* stream) {
+    CMGAN_REQUIRE(dy && x && stats && gamma && dx && dgamma && dbeta, "cmgan_ln_bwd: null pointer");
+    CMGAN_REQUIRE(lddy % 2 == 0 && ldx % 2 == 0 && lddx % 2 == 0 && ldr % 2 == 0 && ldr2 % 2 == 0, "cmgan_ln_bwd: odd leading dimension");
+    if (M == 0) return 0;
+    const int rpw = 16;
+    ln_bwd_kernel<<<cdiv(M, 8 * rpw), 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, reinterpret_cast<const float2*>(stats),
+                                                                     gamma, M, res, ldr, res2, ldr2, dx, lddx, dgamma, dbeta, rpw);
+    return cmgan_check_launch("ln_bwd_kernel");
+}
+
+static int norm_threads(int C) { return C <= 256 ? 256 : C; }
+
+// sums must be zeroed by the caller (G*C*2 doubles).
+CMGAN_API int cmgan_norm_stats(const float* x, long long ldx, int G, long long rows_per_group, int C, double* sums, void* stream) {
+    CMGAN_REQUIRE(x && sums && C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_stats: C=%d unsupported", C);
+    if (G == 0 || rows_per_group == 0) return 0;
+    int nrg = 256 / C;
+    int chunk = nrg * 64;
+    dim3 grid(cdiv(rows_per_group, chunk), G);
+    norm_stats_kernel<<<grid, norm_threads(C), 256 * 2 * sizeof(double), (cudaStream_t)stream>>>(x, ldx, rows_per_group, C, chunk, sums);
+    return cmgan_check_launch("norm_stats_kernel");
+}
+
+CMGAN_API int cmgan_norm_finalize(const double* sums, long long n, int G, int C, int mode, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float* scale, float* shift,
+                                  float* mean_out, float* rstd_out, long long tstride, void* stream) {
+    CMGAN_REQUIRE(gamma && beta && scale && shift, "cmgan_norm_finalize: null pointer");
+    CMGAN_REQUIRE(mode == 1 ? (running_mean && running_var) : (sums != nullptr), "cmgan_norm_finalize: missing statistics");
+    norm_finalize_kernel<<<cdiv((long)G * C, 128), 128, 0, (cudaStream_t)stream>>>(sums, n, G, C, mode, gamma, beta, running_mean,
+                                                                                 running_var, momentum, scale, shift, mean_out,
+                                                                                 rstd_out, tstride);
+    return cmgan_check_launch("norm_finalize_kernel");
+}
+
+// S must be zeroed by the caller (G*C*2 doubles)
+CMGAN_API int cmgan_norm_bwd_reduce(const float* x, long long ldx, const float* dact, long long ldd, int G, long long rows_per_group,
+                                    int C, int act, const float* scale, const float* shift, const float* mean, const float* rstd,
+                                    long long tstride, const float* slope, double* S, float* dslope, void* stream) {
+    CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S, "cmgan_norm_bwd_reduce: null pointer");
+    CMGAN_REQUIRE(C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_bwd_reduce: C=%d unsupported", C);
+    if (G == 0 || rows_per_group == 0) return 0;
+    int nrg = 256 / C;
+    int chunk = nrg * 64;
+    dim3 grid(cdiv(rows_per_group, chunk), G);
+    norm_bwd_reduce_kernel<<<grid, 256, 256 * 3 * sizeof(double), (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, C, chunk, act,
+                                                                                         scale, shift, mean, rstd, tstride, slope, S, dslope);
+    return cmgan_check_launch("norm_bwd_reduce_kernel");
+}
+
+CMGAN_API int cmgan_norm_bwd_apply(const float* x, long long ldx, const float* dact, long long ldd, int G, long long rows_per_group,
+                                   int C, int act, int use_batch_stats, const float* scale, const float* shift, const float* mean,
+                                   const float* rstd, long long tstride, const float* slope, const double* S, float* dx,
+                                   long long lddx, float* dgamma, float* dbeta, void* stream) {
+    CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S && dx, "cmgan_norm_bwd_apply: null pointer");
+    long total = (long)G * rows_per_group * C;
+    if (total == 0) return 0;
+    norm_bwd_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, G, C, act, use_batch_stats,
+                                                                             scale, shift, mean, rstd, tstride, slope, S, dx, lddx,
+                                                                             dgamma, dbeta);
+    return cmgan_check_launch("norm_bwd_apply_kernel");
+}
+
+CMGAN_API int cmgan_norm_apply(const float* x, long long ldx, int G, long long rows_per_group, int C, int act, const float* scale,
+                               const float* shift, long long tstride, const float* slope, float* y, long long ldy, void* stream) {
+    CMGAN_REQUIRE(x && y && scale && shift, "cmgan_norm_apply: null pointer");
+    long total = (long)G * rows_per_group * C;
+    if (total == 0) return 0;
+    norm_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows_per_group, G, C, act, scale, shift, tstride, slope, y, ldy);
+    return cmgan_check_launch("norm_apply_kernel");
+}
+
+CMGAN_API int cmgan_fill(float* p, long long n, float v, void* stream) {
+    if (n == 0) return 0;
+    fill_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+    return cmgan_check_launch("fill_kernel");
+}
+
+CMGAN_API int cmgan_copy_rows(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream) {
+    CMGAN_REQUIRE(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cmgan_copy_rows: bad arguments");
+    if (M == 0) return 0;
+    copy_rows_kernel<<<cdiv(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, M, C);
+    return cmgan_check_launch("copy_rows_kernel");
+}
+
+CMGAN_API int cmgan_add_rows(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream) {
+    CMGAN_REQUIRE(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cmgan_add_rows: bad arguments");
+    if (M == 0) return 0;
+    add_rows_kernel<<<cdiv(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, M, C);
+    return cmgan_check_launch("add_rows_kernel");
+}

@@ -1,0 +1,97 @@
+"""Thin tensor-aware layer over the C ABI: pointer extraction, the GEMM argument block, launch counting.
+
+Nothing here computes: every function forwards to a ``cmgan_*`` entry point of libcmgan_b200.so on the
+current CUDA stream.  PyTorch is used for device memory (``torch.empty``) and the stream handle only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+
+from ._lib import GemmArgs, MAX_TAPS, lib
+
+# number of kernels each entry point launches (for bench.py's ``gpu_launches``)
+_KERNELS = {"cmgan_attention_bwd": 3}
+LAUNCHES = 0
+
+PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
+EPI_NONE, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_DBNSWISH, EPI_ACC = range(5)
+
+Ptr = Union[None, torch.Tensor, Tuple[torch.Tensor, int]]
+
+
+def ptr(t: Ptr) -> Optional[int]:
+    """device address of a tensor, or of element ``off`` of it for a (tensor, off) pair"""
+    if t is None:
+        return None
+    if isinstance(t, tuple):
+        base, off = t
+        return base.data_ptr() + off * base.element_size()
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    """Call a C-ABI entry point; tensors / (tensor, offset) pairs become device pointers; the current
+    stream is appended as the last argument."""
+    global LAUNCHES
+    conv = [ptr(a) if (a is None or isinstance(a, (torch.Tensor, tuple))) else a for a in args]
+    lib().call(name, *conv, stream())
+    LAUNCHES += _KERNELS.get(name, 1)
+
+
+def drop_params(p: float):
+    """(threshold, 1/(1-p)) of the counter-based dropout; p == 0 disables it"""
+    if p <= 0.0:
+        return 0, 1.0
+    return min(int(p * 4294967296.0), 4294967295), 1.0 / (1.0 - p)
+
+
+def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M: int, N: int, Cin: int,
+         sb_tap: int = 0, bias: Ptr = None, taps: Optional[Sequence[Tuple[int, int]]] = None, tap_off: Optional[Sequence[int]] = None,
+         conv: Optional[dict] = None,
+         pro: int = PRO_NONE, pro_alpha: float = 1.0, p0: Ptr = None, p1: Ptr = None, p2: Ptr = None, rows_per_batch: int = 0, pstride: int = 0,
+         epi: int = EPI_NONE, alpha: float = 1.0, R: Ptr = None, ldr: int = 0, aux: Ptr = None, ldaux: int = 0, e0: Ptr = None, e1: Ptr = None,
+         seed: int = 0, drop_p: float = 0.0, pro_seed: int = 0, pro_drop_p: float = 0.0,
+         wgrad: bool = False, D: Ptr = None, ldd: int = 0, prod: int = 0, dbias: Ptr = None, precision: int = 0) -> None:
+    """One dense contraction (see csrc/gemm_args.h).  ``conv`` = dict(OH, OW, IH, IW, mul_y, mul_x, div_y, div_x);
+    ``taps`` = [(dy, dx), ...].  With ``wgrad`` the call accumulates dW (laid out like W) into ``C``."""
+    a = GemmArgs()
+    a.A, a.lda = ptr(A), lda
+    a.B, a.sb_tap, a.sb_k, a.sb_n = ptr(W), sb_tap, sb_k, sb_n
+    a.bias = ptr(bias)
+    a.C, a.ldc = ptr(C), ldc
+    a.M, a.N, a.Cin = M, N, Cin
+    ntaps = len(taps) if taps is not None else (len(tap_off) if tap_off is not None else 1)
+    assert ntaps <= MAX_TAPS
+    a.ntaps = ntaps
+    if conv is not None:
+        a.conv = 1
+        a.OH, a.OW, a.IH, a.IW = conv["OH"], conv["OW"], conv["IH"], conv["IW"]
+        a.mul_y, a.mul_x = conv.get("mul_y", 1), conv.get("mul_x", 1)
+        a.div_y, a.div_x = conv.get("div_y", 1), conv.get("div_x", 1)
+    else:
+        a.conv = 0
+        a.mul_y = a.mul_x = a.div_y = a.div_x = 1
+    for i in range(ntaps):
+        if taps is not None:
+            a.dy[i], a.dx[i] = taps[i]
+        if tap_off is not None:
+            a.tap_off[i] = tap_off[i]
+    a.pro, a.pro_alpha, a.p0, a.p1, a.p2 = pro, pro_alpha, ptr(p0), ptr(p1), ptr(p2)
+    a.rows_per_batch, a.pstride = rows_per_batch, pstride
+    a.epi, a.alpha, a.R, a.ldr, a.aux, a.ldaux, a.e0, a.e1 = epi, alpha, ptr(R), ldr, ptr(aux), ldaux, ptr(e0), ptr(e1)
+    a.seed = seed & 0xFFFFFFFFFFFFFFFF
+    a.drop_thr, a.inv_keep = drop_params(drop_p)
+    a.pro_seed = pro_seed & 0xFFFFFFFFFFFFFFFF
+    a.pro_thr, a.pro_inv_keep = drop_params(pro_drop_p)
+    a.D, a.ldd, a.prod, a.dbias = ptr(D), ldd, prod, ptr(dbias)
+    a.precision = precision
+    global LAUNCHES
+    lib().call("cmgan_gemm_wgrad_f32" if wgrad else "cmgan_gemm_rows_f32", ctypes.byref(a), stream())
+    LAUNCHES += 1
