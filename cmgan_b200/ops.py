@@ -15,6 +15,7 @@ from ._lib import GemmArgs, MAX_TAPS, lib
 # number of kernels each entry point launches (for bench.py's ``gpu_launches``)
 _KERNELS = {"cmgan_attention_bwd": 3}
 LAUNCHES = 0
+PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
 PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
 EPI_NONE, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_DBNSWISH, EPI_ACC = range(5)
@@ -93,5 +94,13 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
     a.D, a.ldd, a.prod, a.dbias = ptr(D), ldd, prod, ptr(dbias)
     a.precision = precision
     global LAUNCHES
-    lib().call("cmgan_gemm_wgrad_f32" if wgrad else "cmgan_gemm_rows_f32", ctypes.byref(a), stream())
+    name = "cmgan_gemm_wgrad_f32" if wgrad else "cmgan_gemm_rows_f32"
+    if PROBE is not None:       # bench.py: CUDA events around every GEMM launch of one instrumented step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib().call(name, ctypes.byref(a), stream())
+        e1.record()
+        PROBE.append((name, M, N, Cin * ntaps, e0, e1))
+    else:
+        lib().call(name, ctypes.byref(a), stream())
     LAUNCHES += 1

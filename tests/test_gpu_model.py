@@ -76,7 +76,7 @@ def test_conformer_block_fwd_bwd(model, g_weights, axis, prefix, B, T, F2):
     _chk(_seq_from_rows(dx.cpu(), B, T, F2, axis), xs64.grad, 2e-5, "conformer dx")
     worst = 0.0
     for k, v in sd64.items():
-        if not v.is_floating_point() or v.grad is None:
+        if not v.is_floating_point() or v.grad is None or "running_" in k:      # buffers are not parameters
             continue
         worst = max(worst, _chk(grads[k], v.grad, 2e-4, "grad " + k))
     print(f"[parity] conformer {prefix}: worst parameter-gradient max-abs {worst:.3e}")
@@ -142,10 +142,13 @@ def test_tscnet_backward_vs_oracle(g_weights, golden):
     print(f"[parity] generator loss {loss.item():.7f} vs oracle {loss_ref.item():.7f} vs reference fixture {float(golden['grad_loss']):.7f}")
     assert abs(loss.item() - loss_ref.item()) < 2e-5
     worst, worst_k = 0.0, ""
+    # a conv bias in front of an InstanceNorm has an exactly-zero gradient: measure every tensor against
+    # max(|its reference gradient|, 1e-3 x the largest gradient entry of the whole model)
+    gmax = max(sd[k].grad.abs().max().item() for k, _ in m.named_parameters())
     for k, p in m.named_parameters():
         ref = sd[k].grad
         assert p.grad is not None, k
-        e = (p.grad.double().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+        e = (p.grad.double().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-3 * gmax)
         if e > worst:
             worst, worst_k = e, k
     print(f"[parity] worst relative parameter-gradient error {worst:.3e} at {worst_k}")
@@ -171,4 +174,4 @@ def test_flat_grad_mode_matches(g_weights, golden):
     for k in grads[0]:
         ref = grads[0][k]
         err = (grads[1][k] - ref).abs().max().item()
-        assert err <= 1e-4 * max(ref.abs().max().item(), 1e-6), f"{k}: {err}"
+        assert err <= 1e-4 * max(ref.abs().max().item(), 1e-3), f"{k}: {err}"      # atomics reorder sums: not bit-exact

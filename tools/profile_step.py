@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""One profiled hot-path step for ncu (run under `ncu --profile-from-start off ...`): the same step bench.py times
+(B x 2 s, generator forward+backward, train mode).  Warm-up steps run outside the cudaProfilerStart/Stop window."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import cmgan_b200  # noqa: E402
+from cmgan_b200 import training  # noqa: E402
+from cmgan_b200.ops import call  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=4)
+ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--fwd-only", action="store_true")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = cmgan_b200.TSCNet(64, 201).to(dev).train()
+flat = model.enable_flat_grads()
+clean, noisy = bench.synth_batch(args.batch, 1000, device=dev)
+
+
+def step():
+    call("cmgan_fill", flat, flat.numel(), 0.0)
+    go = training.forward_generator_step(model, clean, noisy)
+    if args.fwd_only:
+        return
+    training.generator_loss(go, clean).backward()
+
+
+for _ in range(args.warmup):
+    step()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
