@@ -118,9 +118,19 @@ def cpu_weights():
     return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in w.items()}
 
 
+def host_threads():
+    """threads for the CPU arm: the cores this process may run on, capped at 32 (the reference's ~700 small ATen ops per
+    forward stop scaling well before that; 128 threads measured 17x slower than 8 on the GPU box's host)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
 def time_cpu_baseline(n_steps=1, warm=0):
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     sd = cpu_weights()
     clean, noisy = synth_batch(1, 123)
     for _ in range(warm):
@@ -137,7 +147,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     sd = cpu_weights()
     clean, noisy = synth_batch(1, 123)
@@ -290,7 +300,7 @@ def run_ours(args):
             "model_tflops": value * STEP_GFLOP_PER_UTT / 1e3,
         }
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             dt = time_cpu_baseline(1, 0)
             out["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "1 step of B=1 x 2 s (same loss) through the oracle CPU port of the reference, fp32, all host threads"}

@@ -37,6 +37,7 @@ class GemmArgs(ctypes.Structure):
         ("pro_seed", ctypes.c_ulonglong), ("pro_thr", ctypes.c_uint), ("pro_inv_keep", ctypes.c_float),
         ("D", ctypes.c_void_p), ("ldd", ctypes.c_longlong), ("prod", ctypes.c_int), ("dbias", ctypes.c_void_p),
         ("precision", ctypes.c_int),
+        ("ws", ctypes.c_void_p), ("ws_floats", ctypes.c_longlong),
     ]
 
 

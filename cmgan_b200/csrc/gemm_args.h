@@ -50,5 +50,6 @@ typedef struct CmganGemmArgs {
     unsigned long long pro_seed; unsigned int pro_thr; float pro_inv_keep;       // prologue dropout
     // wgrad only: D = upstream gradient rows (M x N), prod: 0 none, 1 = alpha * drop(m*N+n); dbias may be null
     const float* D; long long ldd; int prod; float* dbias;
-    int precision;             // 0 = fp32 FFMA, 1 = tf32 tensor cores (where available)
+    int precision;             // 0 = fp32 FFMA, 1 = tf32 tcgen05 tensor cores (shapes the tensor path does not cover fall back to fp32 FFMA)
+    float* ws; long long ws_floats;   // tf32 path: scratch for the re-tiled weight operand, >= N_pad * Cin * ntaps floats (caller-owned)
 } CmganGemmArgs;

@@ -4,93 +4,13 @@
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_args.h"
+#include "gemm_device.cuh"
 
 namespace {
+using namespace cmgan_gemm;
 
 constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
 constexpr int AS_LD = BM + 4;
-
-struct RowInfo { int b, y, x; bool ok; };
-
-__device__ __forceinline__ RowInfo decode_row(const CmganGemmArgs& g, int m) {
-    RowInfo r;
-    r.ok = m < g.M;
-    if (g.conv) {
-        int x = m % g.OW; int t = m / g.OW;
-        r.x = x; r.y = t % g.OH; r.b = t / g.OH;
-    } else { r.b = 0; r.y = 0; r.x = m; }
-    return r;
-}
-
-// in_row for (row, tap) or -1 when the tap falls into padding / a stride hole
-__device__ __forceinline__ long in_row_of(const CmganGemmArgs& g, const RowInfo& r, int tap) {
-    if (!r.ok) return -1;
-    if (!g.conv) return r.x;
-    int iy = r.y * g.mul_y + g.dy[tap];
-    int ix = r.x * g.mul_x + g.dx[tap];
-    if (iy < 0 || ix < 0) return -1;
-    if (g.div_y > 1) { if (iy % g.div_y) return -1; iy /= g.div_y; }
-    if (g.div_x > 1) { if (ix % g.div_x) return -1; ix /= g.div_x; }
-    if (iy >= g.IH || ix >= g.IW) return -1;
-    return ((long)r.b * g.IH + iy) * g.IW + ix;
-}
-
-__device__ __forceinline__ float apply_pro(const CmganGemmArgs& g, float a, long r, int k, float mean, float rstd) {
-    switch (g.pro) {
-        case CMGAN_PRO_LN: return (a - mean) * rstd * __ldg(g.p1 + k) + __ldg(g.p2 + k);
-        case CMGAN_PRO_SWISH_DROP: return swishf_(a) * cmgan_drop_scale(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
-        case CMGAN_PRO_BN_SWISH: return swishf_(a * __ldg(g.p0 + k) + __ldg(g.p1 + k));
-        case CMGAN_PRO_DROP: return a * g.pro_alpha * cmgan_drop_scale(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
-        case CMGAN_PRO_IN_PRELU: {
-            long b = r / g.rows_per_batch;
-            float z = a * __ldg(g.p0 + b * g.pstride + k) + __ldg(g.p1 + b * g.pstride + k);
-            return z >= 0.f ? z : z * __ldg(g.p2 + k);
-        }
-        default: return a;
-    }
-}
-
-// loads 4 consecutive k of one A row (prologue applied); zeros where masked
-template <int VEC>
-__device__ __forceinline__ void load_a4(const CmganGemmArgs& g, long r, int tap, int k, float out[4]) {
-    out[0] = out[1] = out[2] = out[3] = 0.f;
-    if (r < 0 || k >= g.Cin) return;
-    const float* p = g.A + g.tap_off[tap] + r * g.lda + k;
-    float mean = 0.f, rstd = 0.f;
-    if (g.pro == CMGAN_PRO_LN) { float2 st = __ldg(reinterpret_cast<const float2*>(g.p0) + r); mean = st.x; rstd = st.y; }
-    if (VEC == 4 && k + 3 < g.Cin) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(p));
-        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-        if (g.pro != CMGAN_PRO_NONE) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) out[i] = apply_pro(g, out[i], r, k + i, mean, rstd);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (k + i < g.Cin) out[i] = apply_pro(g, __ldg(p + i), r, k + i, mean, rstd);
-    }
-}
-
-__device__ __forceinline__ float epilogue(const CmganGemmArgs& g, float v, long m, int n, const float* cptr) {
-    switch (g.epi) {
-        case CMGAN_EPI_DROP_RES: {
-            float o = g.alpha * v * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
-            if (g.R) o += __ldg(g.R + m * g.ldr + n);
-            return o;
-        }
-        case CMGAN_EPI_DSWISH_DROP: {
-            float h = __ldg(g.aux + m * g.ldaux + n);
-            return v * dswishf_(h) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
-        }
-        case CMGAN_EPI_DBNSWISH: {
-            float z = __ldg(g.aux + m * g.ldaux + n) * __ldg(g.e0 + n) + __ldg(g.e1 + n);
-            return v * dswishf_(z);
-        }
-        case CMGAN_EPI_ACC: return g.alpha * v + *cptr;
-        default: return v;
-    }
-}
 
 template <int VEC>
 __global__ void __launch_bounds__(NT, 2) gemm_rows_kernel(const __grid_constant__ CmganGemmArgs g) {
@@ -263,6 +183,8 @@ int validate(const CmganGemmArgs* a, const char* who) {
 
 }  // namespace
 
+int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st);   // gemm_tc.cu
+
 // C[M, N] = epi(bias + sum_taps pro(A) * B); see gemm_args.h.  Replaces every nn.Linear / nn.Conv1d(k=1) /
 // nn.Conv2d of reference generator.py:24-32,53-63,108 and conformer.py:82-84,140-144,163,173 and their
 // autograd data gradients.
@@ -271,6 +193,10 @@ CMGAN_API int cmgan_gemm_rows_f32(const CmganGemmArgs* a, void* stream) {
     CMGAN_REQUIRE(a->B != nullptr, "cmgan_gemm_rows_f32: null B");
     if (a->M == 0) return 0;
     if (a->epi == CMGAN_EPI_DSWISH_DROP || a->epi == CMGAN_EPI_DBNSWISH) CMGAN_REQUIRE(a->aux != nullptr, "gemm_rows: epilogue needs aux");
+    if (a->precision == 1) {                       // tf32 tcgen05 path (gemm_tc.cu); 1 = shape not covered -> exact fp32 path below
+        int rc = cmgan_gemm_rows_tc_launch(a, (cudaStream_t)stream);
+        if (rc <= 0) return rc;
+    }
     dim3 grid(cdiv(a->M, BM), cdiv(a->N, BN));
     if (vec_ok(*a)) gemm_rows_kernel<4><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
     else gemm_rows_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);

@@ -6,6 +6,7 @@ current CUDA stream.  PyTorch is used for device memory (``torch.empty``) and th
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple, Union
 
 import torch
@@ -15,6 +16,7 @@ from ._lib import GemmArgs, MAX_TAPS, lib
 # number of kernels each entry point launches (for bench.py's ``gpu_launches``)
 _KERNELS = {"cmgan_attention_bwd": 3}
 LAUNCHES = 0
+PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" else 0   # default for every dense contraction
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
 PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
@@ -46,6 +48,13 @@ def call(name: str, *args) -> None:
     LAUNCHES += _KERNELS.get(name, 1)
 
 
+def set_precision(mode: str) -> None:
+    """'fp32' (exact FFMA) or 'tf32' (tcgen05 tensor cores for the dense contractions; fp32 storage, fp32 accumulate)"""
+    global PRECISION
+    assert mode in ("fp32", "tf32")
+    PRECISION = 1 if mode == "tf32" else 0
+
+
 def drop_params(p: float):
     """(threshold, 1/(1-p)) of the counter-based dropout; p == 0 disables it"""
     if p <= 0.0:
@@ -59,7 +68,7 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
          pro: int = PRO_NONE, pro_alpha: float = 1.0, p0: Ptr = None, p1: Ptr = None, p2: Ptr = None, rows_per_batch: int = 0, pstride: int = 0,
          epi: int = EPI_NONE, alpha: float = 1.0, R: Ptr = None, ldr: int = 0, aux: Ptr = None, ldaux: int = 0, e0: Ptr = None, e1: Ptr = None,
          seed: int = 0, drop_p: float = 0.0, pro_seed: int = 0, pro_drop_p: float = 0.0,
-         wgrad: bool = False, D: Ptr = None, ldd: int = 0, prod: int = 0, dbias: Ptr = None, precision: int = 0) -> None:
+         wgrad: bool = False, D: Ptr = None, ldd: int = 0, prod: int = 0, dbias: Ptr = None, precision: Optional[int] = None) -> None:
     """One dense contraction (see csrc/gemm_args.h).  ``conv`` = dict(OH, OW, IH, IW, mul_y, mul_x, div_y, div_x);
     ``taps`` = [(dy, dx), ...].  With ``wgrad`` the call accumulates dW (laid out like W) into ``C``."""
     a = GemmArgs()
@@ -92,7 +101,11 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
     a.pro_seed = pro_seed & 0xFFFFFFFFFFFFFFFF
     a.pro_thr, a.pro_inv_keep = drop_params(pro_drop_p)
     a.D, a.ldd, a.prod, a.dbias = ptr(D), ldd, prod, ptr(dbias)
-    a.precision = precision
+    a.precision = PRECISION if precision is None else precision
+    ws = None
+    if a.precision == 1 and not wgrad and N % 16 == 0 and N <= 256 and Cin % 32 == 0:
+        ws = torch.empty(N * Cin * ntaps, dtype=torch.float32, device=(A[0] if isinstance(A, tuple) else A).device)
+        a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
     global LAUNCHES
     name = "cmgan_gemm_wgrad_f32" if wgrad else "cmgan_gemm_rows_f32"
     if PROBE is not None:       # bench.py: CUDA events around every GEMM launch of one instrumented step
@@ -103,4 +116,4 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
         PROBE.append((name, M, N, Cin * ntaps, e0, e1))
     else:
         lib().call(name, ctypes.byref(a), stream())
-    LAUNCHES += 1
+    LAUNCHES += 2 if ws is not None else 1
