@@ -170,7 +170,7 @@ def run_reference(args):
 
 def workload_name(B):
     return (f"generator fwd+bwd (train mode: dropout + BatchNorm batch stats), stft->compress->TSCNet->uncompress->istft->loss, "
-            f"batch {B} x 2 s @16 kHz per GPU, fp32")
+            f"batch {B} x 2 s @16 kHz per GPU, fp32 storage")
 
 
 # ------------------------------------------------------------------------------------------------ our arm (GPU)
@@ -178,6 +178,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import cmgan_b200
+    from cmgan_b200 import ops as _ops
+    _ops.set_precision(args.precision)
     from cmgan_b200 import ops, training
     from cmgan_b200.ops import call
 
@@ -288,7 +290,7 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(B), "global_batch": B * world, "clip_samples": CLIP, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
                        "weights": "torch.manual_seed(0) default init"},
@@ -317,6 +319,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="dense contractions: tcgen05 tf32 (default) or exact fp32 FFMA")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

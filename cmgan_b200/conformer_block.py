@@ -1,0 +1,219 @@
+"""Conformer block (macaron FFN - MHSA with Shaw relative positions - convolution module - FFN - LayerNorm) over the CUDA
+kernels: forward and hand-written backward orchestration (ref: conformer.py:182-222, generator.py:92-99).
+
+Rows are channel-last (b, t, f) x 64; a block processes either all time sequences (axis 0) or all frequency sequences
+(axis 1) of the (B, T, F2) grid without ever transposing: only the attention and depthwise-convolution kernels look at
+the sequence axis.  Helper classes for normalisation tables / statistics scratch live here too.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import (EPI_ACC, EPI_DBNSWISH, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_NONE, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU, PRO_LN,
+                  PRO_SWISH_DROP, call, gemm)
+
+C = 64          # num_channel (the kernels are specialised for 64 channels = 4 heads x 16)
+CAT = 5 * C     # width of a dense-block concat buffer: [out4 | out3 | out2 | out1 | x]
+FF_DROP = 0.2   # ref: generator.py:82,89
+ATT_DROP = 0.2  # ref: generator.py:81,88
+
+
+def _empty(*shape, dev, dtype=torch.float32):
+    return torch.empty(*shape, dtype=dtype, device=dev)
+
+
+class _Tabs:
+    """scale/shift/mean/rstd per (group, channel) and PReLU slope per channel of a normalisation site
+    (or of all five 64-channel slots of a dense-block concat buffer)."""
+
+    def __init__(self, G, width, dev, identity=False):
+        self.scale = _empty(G, width, dev=dev)
+        self.shift = _empty(G, width, dev=dev)
+        self.mean = _empty(G, width, dev=dev)
+        self.rstd = _empty(G, width, dev=dev)
+        self.slope = _empty(width, dev=dev)
+        self.width = width
+        if identity:    # slot 4 of a decoder concat buffer holds final activations: act(x) = x
+            call("cmgan_fill", self.scale, G * width, 1.0)
+            call("cmgan_fill", self.shift, G * width, 0.0)
+            call("cmgan_fill", self.slope, width, 1.0)
+
+
+class _Sums:
+    """One zero-initialised double scratch per pass, sliced per statistics site (a single memset)."""
+
+    def __init__(self, n, dev):
+        self.buf = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.off = 0
+
+    def take(self, n):
+        assert self.off + n <= self.buf.numel(), "statistics scratch exhausted"
+        o = self.off
+        self.off += n
+        return (self.buf, o)
+
+
+def _inst_norm_site(x, ldx, G, rows, Cn, gamma, beta, tabs: _Tabs, c0, slope_w, sums: _Sums):
+    """InstanceNorm2d statistics (ref: generator.py:35) -> tables at channel offset c0 of ``tabs``"""
+    s = sums.take(G * Cn * 2)
+    call("cmgan_norm_stats", x, ldx, G, rows, Cn, s)
+    call("cmgan_norm_finalize", s, rows, G, Cn, 0, gamma, beta, None, None, 0.0, (tabs.scale, c0), (tabs.shift, c0), (tabs.mean, c0),
+         (tabs.rstd, c0), tabs.width)
+    if slope_w is not None:
+        call("cmgan_copy_rows", slope_w, Cn, (tabs.slope, c0), Cn, 1, Cn)
+
+
+def _norm_bwd(x, ldx, dact, ldd, G, rows, Cn, act, batch_stats, tabs: _Tabs, c0, slope, dx, lddx, dgamma, dbeta, dslope, sums: _Sums):
+    s = sums.take(G * Cn * 2)
+    args = ((tabs.scale, c0), (tabs.shift, c0), (tabs.mean, c0), (tabs.rstd, c0), tabs.width, slope)
+    call("cmgan_norm_bwd_reduce", x, ldx, dact, ldd, G, rows, Cn, act, *args, s, dslope)
+    call("cmgan_norm_bwd_apply", x, ldx, dact, ldd, G, rows, Cn, act, 1 if batch_stats else 0, *args, s, dx, lddx, dgamma, dbeta)
+
+
+def _site_seed(seed: int, block_id: int, site: int) -> int:
+    return (seed * 1000003 + block_id * 16 + site + 1) & 0xFFFFFFFFFFFFFFFF
+
+
+# ====================================================================================== conformer block
+def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums, save: Optional[dict]):
+    """ConformerBlock + the outer TSCB residual (ref: conformer.py:216-222, generator.py:95,97).
+    x: (M, 64) rows of the (B, T, F2) grid; axis 0 = sequences along T, 1 = along F2.  Returns LN(x4) + x."""
+    dev = x.device
+    M = x.shape[0]
+    dp = FF_DROP if training else 0.0
+    da = ATT_DROP if training else 0.0
+    sd = [_site_seed(seed, block_id, i) for i in range(5)]
+
+    def ff(xin, name, s1, s2):
+        st = _empty(M, 2, dev=dev)
+        call("cmgan_ln_stats", xin, C, M, st)
+        h = _empty(M, 4 * C, dev=dev)
+        gemm(A=xin, lda=C, W=P[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.{name}.fn.fn.net.0.bias"], C=h, ldc=4 * C, M=M,
+             N=4 * C, Cin=C, pro=PRO_LN, p0=st, p1=P[f"{p}.{name}.fn.norm.weight"], p2=P[f"{p}.{name}.fn.norm.bias"])
+        out = _empty(M, C, dev=dev)
+        gemm(A=h, lda=4 * C, W=P[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, bias=P[f"{p}.{name}.fn.fn.net.3.bias"], C=out, ldc=C, M=M,
+             N=C, Cin=4 * C, pro=PRO_SWISH_DROP, pro_seed=s1, pro_drop_p=dp, epi=EPI_DROP_RES, alpha=0.5, R=xin, ldr=C, seed=s2, drop_p=dp)
+        return st, h, out
+
+    st1, h1, x1 = ff(x, "ff1", sd[0], sd[1])
+    # ---- attention (ref: conformer.py:90-133)
+    st2 = _empty(M, 2, dev=dev)
+    call("cmgan_ln_stats", x1, C, M, st2)
+    qkv = _empty(M, 3 * C, dev=dev)
+    lnw, lnb = P[f"{p}.attn.norm.weight"], P[f"{p}.attn.norm.bias"]
+    gemm(A=x1, lda=C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, C=qkv, ldc=3 * C, M=M, N=C, Cin=C, pro=PRO_LN, p0=st2, p1=lnw, p2=lnb)
+    gemm(A=x1, lda=C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, C=(qkv, C), ldc=3 * C, M=M, N=2 * C, Cin=C, pro=PRO_LN, p0=st2, p1=lnw,
+         p2=lnb)
+    ctx = _empty(M, C, dev=dev)
+    lse = _empty(M, 4, dev=dev)
+    call("cmgan_attention_fwd", qkv, P[f"{p}.attn.fn.rel_pos_emb.weight"], B, T, F2, axis, ctx, lse)
+    x2 = _empty(M, C, dev=dev)
+    gemm(A=ctx, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.attn.fn.to_out.bias"], C=x2, ldc=C, M=M, N=C, Cin=C,
+         epi=EPI_DROP_RES, alpha=1.0, R=x1, ldr=C, seed=sd[2], drop_p=da)
+    # ---- convolution module (ref: conformer.py:160-173)
+    st3 = _empty(M, 2, dev=dev)
+    call("cmgan_ln_stats", x2, C, M, st3)
+    g = _empty(M, 4 * C, dev=dev)
+    gemm(A=x2, lda=C, W=P[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.conv.net.2.bias"], C=g, ldc=4 * C, M=M, N=4 * C, Cin=C,
+         pro=PRO_LN, p0=st3, p1=P[f"{p}.conv.net.0.weight"], p2=P[f"{p}.conv.net.0.bias"])
+    d = _empty(M, 2 * C, dev=dev)
+    call("cmgan_glu_dwconv_fwd", g, P[f"{p}.conv.net.4.conv.weight"], P[f"{p}.conv.net.4.conv.bias"], B, T, F2, axis, d)
+    bn = _Tabs(1, 2 * C, dev)
+    bnp = (P[f"{p}.conv.net.5.weight"], P[f"{p}.conv.net.5.bias"], P[f"{p}.conv.net.5.running_mean"], P[f"{p}.conv.net.5.running_var"])
+    if training:
+        s = sums.take(2 * C * 2)
+        call("cmgan_norm_stats", d, 2 * C, 1, M, 2 * C, s)
+        call("cmgan_norm_finalize", s, M, 1, 2 * C, 0, *bnp, 0.1, bn.scale, bn.shift, bn.mean, bn.rstd, 2 * C)
+    else:
+        call("cmgan_norm_finalize", None, M, 1, 2 * C, 1, *bnp, 0.1, bn.scale, bn.shift, bn.mean, bn.rstd, 2 * C)
+    x3 = _empty(M, C, dev=dev)
+    gemm(A=d, lda=2 * C, W=P[f"{p}.conv.net.7.weight"], sb_k=1, sb_n=2 * C, bias=P[f"{p}.conv.net.7.bias"], C=x3, ldc=C, M=M, N=C, Cin=2 * C,
+         pro=PRO_BN_SWISH, p0=bn.scale, p1=bn.shift, epi=EPI_DROP_RES, alpha=1.0, R=x2, ldr=C)
+    # ---- second feed-forward, post norm, outer residual
+    st4, h2, x4 = ff(x3, "ff2", sd[3], sd[4])
+    st5 = _empty(M, 2, dev=dev)
+    y = _empty(M, C, dev=dev)
+    call("cmgan_ln_apply", x4, C, M, P[f"{p}.post_norm.weight"], P[f"{p}.post_norm.bias"], x, C, y, C, st5)
+    if save is not None:
+        save.update(x=x, st1=st1, h1=h1, x1=x1, st2=st2, qkv=qkv, ctx=ctx, lse=lse, x2=x2, st3=st3, g=g, d=d, bn=bn, x3=x3, st4=st4, h2=h2,
+                    x4=x4, st5=st5, sd=sd, dp=dp, da=da, axis=axis, training=training, p=p)
+    return y
+
+
+def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _Sums):
+    """Gradient of conformer_fwd: dy (M, 64) -> dx (M, 64); parameter gradients accumulate into G[name]."""
+    dev = dy.device
+    M = dy.shape[0]
+    p, axis, dp, da, sd = S["p"], S["axis"], S["dp"], S["da"], S["sd"]
+
+    def ff_bwd(dout, xin, st, h, name, s1, s2, res2=None):
+        # out = xin + 0.5 * drop2(W2 (swish(h) * drop1) + b2),  h = W1 LN(xin) + b1
+        W1, W2 = P[f"{p}.{name}.fn.fn.net.0.weight"], P[f"{p}.{name}.fn.fn.net.3.weight"]
+        dh = _empty(M, 4 * C, dev=dev)
+        gemm(A=dout, lda=C, W=W2, sb_k=4 * C, sb_n=1, C=dh, ldc=4 * C, M=M, N=4 * C, Cin=C, pro=PRO_DROP, pro_alpha=0.5, pro_seed=s2,
+             pro_drop_p=dp, epi=EPI_DSWISH_DROP, aux=h, ldaux=4 * C, seed=s1, drop_p=dp)
+        gemm(wgrad=True, A=h, lda=4 * C, Cin=4 * C, pro=PRO_SWISH_DROP, pro_seed=s1, pro_drop_p=dp, D=dout, ldd=C, N=C, prod=1, alpha=0.5, seed=s2,
+             drop_p=dp, W=None, C=G[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.3.bias"])
+        dln = _empty(M, C, dev=dev)
+        gemm(A=dh, lda=4 * C, W=W1, sb_k=C, sb_n=1, C=dln, ldc=C, M=M, N=C, Cin=4 * C)
+        gemm(wgrad=True, A=xin, lda=C, Cin=C, pro=PRO_LN, p0=st, p1=P[f"{p}.{name}.fn.norm.weight"], p2=P[f"{p}.{name}.fn.norm.bias"], D=dh,
+             ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.0.bias"])
+        dxin = _empty(M, C, dev=dev)
+        call("cmgan_ln_bwd", dln, C, xin, C, st, P[f"{p}.{name}.fn.norm.weight"], M, dout, C, res2, C, dxin, C, G[f"{p}.{name}.fn.norm.weight"],
+             G[f"{p}.{name}.fn.norm.bias"])
+        return dxin
+
+    # y = LN(x4) * g + b + x
+    dx4 = _empty(M, C, dev=dev)
+    call("cmgan_ln_bwd", dy, C, S["x4"], C, S["st5"], P[f"{p}.post_norm.weight"], M, None, 0, None, 0, dx4, C, G[f"{p}.post_norm.weight"],
+         G[f"{p}.post_norm.bias"])
+    dx3 = ff_bwd(dx4, S["x3"], S["st4"], S["h2"], "ff2", sd[3], sd[4])
+    # ---- convolution module: x3 = x2 + W7 swish(bn(d)) + b7
+    bn = S["bn"]
+    dbn = _empty(M, 2 * C, dev=dev)
+    gemm(A=dx3, lda=C, W=P[f"{p}.conv.net.7.weight"], sb_k=2 * C, sb_n=1, C=dbn, ldc=2 * C, M=M, N=2 * C, Cin=C, epi=EPI_DBNSWISH, aux=S["d"],
+         ldaux=2 * C, e0=bn.scale, e1=bn.shift)
+    gemm(wgrad=True, A=S["d"], lda=2 * C, Cin=2 * C, pro=PRO_BN_SWISH, p0=bn.scale, p1=bn.shift, D=dx3, ldd=C, N=C, W=None,
+         C=G[f"{p}.conv.net.7.weight"], sb_k=1, sb_n=2 * C, ldc=0, M=M, dbias=G[f"{p}.conv.net.7.bias"])
+    dd = _empty(M, 2 * C, dev=dev)
+    _norm_bwd(S["d"], 2 * C, dbn, 2 * C, 1, M, 2 * C, 0, S["training"], bn, 0, None, dd, 2 * C, G[f"{p}.conv.net.5.weight"],
+              G[f"{p}.conv.net.5.bias"], None, sums)
+    dg = _empty(M, 4 * C, dev=dev)
+    call("cmgan_glu_dwconv_bwd", S["g"], dd, P[f"{p}.conv.net.4.conv.weight"], B, T, F2, axis, dg, G[f"{p}.conv.net.4.conv.weight"],
+         G[f"{p}.conv.net.4.conv.bias"])
+    dln3 = _empty(M, C, dev=dev)
+    gemm(A=dg, lda=4 * C, W=P[f"{p}.conv.net.2.weight"], sb_k=C, sb_n=1, C=dln3, ldc=C, M=M, N=C, Cin=4 * C)
+    gemm(wgrad=True, A=S["x2"], lda=C, Cin=C, pro=PRO_LN, p0=S["st3"], p1=P[f"{p}.conv.net.0.weight"], p2=P[f"{p}.conv.net.0.bias"], D=dg,
+         ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.conv.net.2.bias"])
+    dx2 = _empty(M, C, dev=dev)
+    call("cmgan_ln_bwd", dln3, C, S["x2"], C, S["st3"], P[f"{p}.conv.net.0.weight"], M, dx3, C, None, 0, dx2, C, G[f"{p}.conv.net.0.weight"],
+         G[f"{p}.conv.net.0.bias"])
+    # ---- attention: x2 = x1 + drop(ctx Wo^T + bo)
+    dctx = _empty(M, C, dev=dev)
+    gemm(A=dx2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C, pro=PRO_DROP, pro_alpha=1.0,
+         pro_seed=sd[2], pro_drop_p=da)
+    gemm(wgrad=True, A=S["ctx"], lda=C, Cin=C, D=dx2, ldd=C, N=C, prod=1, alpha=1.0, seed=sd[2], drop_p=da, W=None,
+         C=G[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.attn.fn.to_out.bias"])
+    dqkv = _empty(M, 3 * C, dev=dev)
+    delta = _empty(M, 4, dev=dev)
+    call("cmgan_attention_bwd", S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv,
+         G[f"{p}.attn.fn.rel_pos_emb.weight"])
+    dln2 = _empty(M, C, dev=dev)
+    gemm(A=dqkv, lda=3 * C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=C)
+    gemm(A=(dqkv, C), lda=3 * C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=2 * C, epi=EPI_ACC, alpha=1.0)
+    lnw, lnb = P[f"{p}.attn.norm.weight"], P[f"{p}.attn.norm.bias"]
+    gemm(wgrad=True, A=S["x1"], lda=C, Cin=C, pro=PRO_LN, p0=S["st2"], p1=lnw, p2=lnb, D=dqkv, ldd=3 * C, N=C, W=None,
+         C=G[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
+    gemm(wgrad=True, A=S["x1"], lda=C, Cin=C, pro=PRO_LN, p0=S["st2"], p1=lnw, p2=lnb, D=(dqkv, C), ldd=3 * C, N=2 * C, W=None,
+         C=G[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
+    dx1 = _empty(M, C, dev=dev)
+    call("cmgan_ln_bwd", dln2, C, S["x1"], C, S["st2"], lnw, M, dx2, C, None, 0, dx1, C, G[f"{p}.attn.norm.weight"], G[f"{p}.attn.norm.bias"])
+    # ---- first feed-forward; the outer residual adds dy
+    return ff_bwd(dx1, S["x"], S["st1"], S["h1"], "ff1", sd[0], sd[1], res2=dy)
+
+

@@ -1,10 +1,14 @@
 // tf32 tensor-core implementation of the row-parallel GEMM contract (gemm_args.h) for sm_100a:
 // tcgen05.mma (kind::tf32, M = 128, N = 16..256) with the accumulator in TMEM, warp-specialised:
 //
-//   warps 0-3  A producers, then epilogue.  global (LDG.128, gathered rows of the implicit convolution) -> registers
-//              -> prologue (LayerNorm / InstanceNorm+PReLU / BatchNorm+Swish / Swish+dropout) -> round to tf32 ->
-//              st.shared in the canonical K-major SWIZZLE_128B layout -> fence.proxy.async -> mbarrier arrive.
-//              After the main loop the same warps read the accumulator (tcgen05.ld 32x32b) and run the fused epilogue.
+//   warps 0-3  A producers, then epilogue.
+//              * no prologue (convolutions over materialised activations, data gradients): cp.async (LDGSTS, 16 B, zero-fill for
+//                padding rows) straight into the canonical K-major SWIZZLE_128B layout, software-pipelined two chunks deep;
+//                a chunk is published with cp.async.wait_group -> fence.proxy.async -> mbarrier.arrive.
+//              * with prologue (LayerNorm / BatchNorm+Swish / Swish+dropout / dropout): LDG.128 -> registers -> transform
+//                (per-chunk parameters hoisted into float4 registers) -> round to tf32 -> st.shared -> fence -> arrive.
+//              After the main loop the same warps drain the accumulator: tcgen05.ld 32x32b -> shared-memory staging ->
+//              coalesced float4 epilogue (bias, dropout, residual, activation gradients) -> global.
 //   warp 4     TMEM allocation; one lane issues tcgen05.mma and tcgen05.commit (stage release / accumulator ready).
 //   warp 5     one lane issues the weight-tile loads: cp.async.bulk (TMA bulk copy, UBLKCP) of a pre-tiled,
 //              pre-swizzled (N x 128 B) block per K chunk, completing on the stage's mbarrier.
@@ -25,6 +29,8 @@ constexpr int KC = 32;               // floats per K chunk = one 128-byte swizzl
 constexpr int A_STAGE_BYTES = BM * KC * 4;   // 16 KB
 constexpr int NPROD = 128;           // producer / epilogue threads (warps 0-3)
 constexpr int NTHREADS = 192;
+constexpr int SLAB = 64;             // epilogue column slab
+constexpr int STG_LD = SLAB + 4;     // staging row stride (floats): conflict-free 128-bit accesses
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,6 +61,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -116,13 +129,63 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
     out[(chunk * BN + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
 }
 
-// ---- main kernel --------------------------------------------------------------------------------------
-struct SmemLayout { int stages; int b_stage_bytes; };
+// ---- prologue on 4 consecutive k with hoisted per-chunk parameters -----------------------------------
+struct ChunkParams { float4 a, b; };     // LN: gamma, beta;  BN: scale, shift
 
+__device__ __forceinline__ void load_chunk_params(const CmganGemmArgs& g, int k, ChunkParams& cp) {
+    if (g.pro == CMGAN_PRO_LN) { cp.a = __ldg(reinterpret_cast<const float4*>(g.p1 + k)); cp.b = __ldg(reinterpret_cast<const float4*>(g.p2 + k)); }
+    else if (g.pro == CMGAN_PRO_BN_SWISH) { cp.a = __ldg(reinterpret_cast<const float4*>(g.p0 + k)); cp.b = __ldg(reinterpret_cast<const float4*>(g.p1 + k)); }
+}
+
+__device__ __forceinline__ float4 transform4(const CmganGemmArgs& g, float4 v, long r, int k, float mean, float rstd, const ChunkParams& cp) {
+    switch (g.pro) {
+        case CMGAN_PRO_LN:
+            v.x = (v.x - mean) * rstd * cp.a.x + cp.b.x; v.y = (v.y - mean) * rstd * cp.a.y + cp.b.y;
+            v.z = (v.z - mean) * rstd * cp.a.z + cp.b.z; v.w = (v.w - mean) * rstd * cp.a.w + cp.b.w;
+            break;
+        case CMGAN_PRO_BN_SWISH:
+            v.x = swishf_(fmaf(v.x, cp.a.x, cp.b.x)); v.y = swishf_(fmaf(v.y, cp.a.y, cp.b.y));
+            v.z = swishf_(fmaf(v.z, cp.a.z, cp.b.z)); v.w = swishf_(fmaf(v.w, cp.a.w, cp.b.w));
+            break;
+        case CMGAN_PRO_SWISH_DROP: {
+            v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
+            if (g.pro_thr) {
+                uint64_t idx = (uint64_t)r * g.Cin + k;
+                v.x *= cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep); v.y *= cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
+                v.z *= cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep); v.w *= cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
+            }
+            break;
+        }
+        case CMGAN_PRO_DROP: {
+            uint64_t idx = (uint64_t)r * g.Cin + k;
+            v.x *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep);
+            v.y *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
+            v.z *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep);
+            v.w *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
+            break;
+        }
+        case CMGAN_PRO_IN_PRELU: {
+            long b = r / g.rows_per_batch;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.p0 + b * g.pstride + k));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(g.p1 + b * g.pstride + k));
+            const float4 sl = __ldg(reinterpret_cast<const float4*>(g.p2 + k));
+            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            v.x = v.x >= 0.f ? v.x : v.x * sl.x; v.y = v.y >= 0.f ? v.y : v.y * sl.y;
+            v.z = v.z >= 0.f ? v.z : v.z * sl.z; v.w = v.w >= 0.f ? v.w : v.w * sl.w;
+            break;
+        }
+        default: break;
+    }
+    return v;
+}
+
+// ---- main kernel --------------------------------------------------------------------------------------
+template <bool ASYNC_A>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
                                                                     int BN, int stages, int tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int b_stage_bytes = BN * KC * 4;
     const uint32_t sA = base;
     const uint32_t sB = base + stages * A_STAGE_BYTES;
@@ -156,52 +219,119 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_rows_tc_kernel(const __grid_
         RowInfo ri[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ri[i] = decode_row(g, m0 + rr + 16 * i);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % stages;
-            const uint32_t par = (uint32_t)((ch / stages) & 1);
-            const int tap = ch / cpt, k0 = (ch - tap * cpt) * KC + c * 4;
-            float v[8][4];
+        uint32_t dst_off[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) load_a4<4>(g, in_row_of(g, ri[i], tap), tap, k0, v[i]);
-            mbar_wait(empty_bar(s), par ^ 1u);
+        for (int i = 0; i < 8; ++i) { const int r = rr + 16 * i; dst_off[i] = r * 128 + ((c ^ (r & 7)) << 4); }
+
+        if (ASYNC_A) {
+            // ---- cp.async pipeline: issue chunk ch, publish chunk ch - LAG
+            const int LAG = stages >= 3 ? 2 : 1;
+            long rowoff[8];                // element offset of the gathered row for the current tap, -1 = padding
+            int cur_tap = -1;
+            for (int ch = 0; ch < nchunks + LAG; ++ch) {
+                if (ch < nchunks) {
+                    const int s = ch % stages;
+                    const uint32_t par = (uint32_t)((ch / stages) & 1);
+                    const int tap = ch / cpt, k0 = (ch - tap * cpt) * KC + c * 4;
+                    if (tap != cur_tap) {
+                        cur_tap = tap;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rr + 16 * i;
-                const uint32_t dst = sA + s * A_STAGE_BYTES + r * 128 + ((c ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(to_tf32(v[i][0])), "f"(to_tf32(v[i][1])),
-                             "f"(to_tf32(v[i][2])), "f"(to_tf32(v[i][3])) : "memory");
+                        for (int i = 0; i < 8; ++i) {
+                            long r = in_row_of(g, ri[i], tap);
+                            rowoff[i] = r < 0 ? -1 : g.tap_off[tap] + r * g.lda;
+                        }
+                    }
+                    mbar_wait(empty_bar(s), par ^ 1u);
+                    const uint32_t sbase = sA + s * A_STAGE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = rowoff[i] >= 0;
+                        cp_async16(sbase + dst_off[i], g.A + (ok ? rowoff[i] + k0 : 0), ok ? 16u : 0u);
+                    }
+                }
+                cp_async_commit();
+                const int done = ch - LAG;
+                if (done >= 0) {
+                    if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                    fence_proxy_async();
+                    mbar_arrive(full_bar(done % stages));
+                }
             }
-            fence_proxy_async();
-            mbar_arrive(full_bar(s));
+        } else {
+            // ---- register path with prologue
+            float mean[8], rstd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { mean[i] = 0.f; rstd[i] = 1.f; }
+            if (g.pro == CMGAN_PRO_LN) {        // ntaps == 1: in_row is constant over the K loop
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    long r = in_row_of(g, ri[i], 0);
+                    if (r >= 0) { float2 st = __ldg(reinterpret_cast<const float2*>(g.p0) + r); mean[i] = st.x; rstd[i] = st.y; }
+                }
+            }
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int s = ch % stages;
+                const uint32_t par = (uint32_t)((ch / stages) & 1);
+                const int tap = ch / cpt, k0 = (ch - tap * cpt) * KC + c * 4;
+                ChunkParams cp;
+                load_chunk_params(g, k0, cp);
+                float4 v[8];
+                long rows[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    rows[i] = in_row_of(g, ri[i], tap);
+                    v[i] = rows[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(g.A + g.tap_off[tap] + rows[i] * g.lda + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (rows[i] >= 0) v[i] = transform4(g, v[i], rows[i], k0, mean[i], rstd[i], cp);
+                mbar_wait(empty_bar(s), par ^ 1u);
+                const uint32_t sbase = sA + s * A_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + dst_off[i]), "f"(to_tf32(v[i].x)), "f"(to_tf32(v[i].y)),
+                                 "f"(to_tf32(v[i].z)), "f"(to_tf32(v[i].w)) : "memory");
+                fence_proxy_async();
+                mbar_arrive(full_bar(s));
+            }
         }
         // ================================ epilogue ================================
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const long m = (long)m0 + warp * 32 + lane;
+        // all MMAs have completed -> the pipeline stages are free: reuse them as per-warp staging (32 rows x 68 floats)
+        float* stg = reinterpret_cast<float*>(base_ptr) + warp * 32 * STG_LD;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int n0 = 0; n0 < BN; n0 += 16) {
-            float acc[16];
-            tmem_ld16(trow + (uint32_t)n0, acc);
-            if (m < g.M) {
-                float* cp = g.C + m * g.ldc + n0;
+        const int col4 = (lane & 15) * 4;          // this lane's 4 columns within the slab
+        const int rsub = lane >> 4;                // 0/1: two rows per pass
+        for (int n0 = 0; n0 < BN; n0 += SLAB) {
+            const int ncols = min(SLAB, BN - n0);
+            for (int q = 0; q < ncols; q += 16) {
+                float acc[16];
+                tmem_ld16(trow + (uint32_t)(n0 + q), acc);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + j;
-                    if (n < g.N) {
-                        float vv = acc[j] + (g.bias ? __ldg(g.bias + n) : 0.f);
-                        acc[j] = epilogue(g, vv, m, n, cp + j);
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + q + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+            __syncwarp();
+            const int n = n0 + col4;
+            if (col4 < ncols) {
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                for (int rp = 0; rp < 32; rp += 2) {
+                    const int rl = rp + rsub;
+                    const long m = (long)m0 + warp * 32 + rl;
+                    if (m >= g.M) continue;
+                    float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
+                    float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
+                    float* cp = g.C + m * g.ldc + n;
+                    if (g.epi != CMGAN_EPI_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) vv[j] = epilogue(g, vv[j], m, n + j, cp + j);
                     }
-                }
-                if (n0 + 16 <= g.N && (g.ldc & 3) == 0 && (((uintptr_t)g.C) & 15) == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < g.N) cp[j] = acc[j];
+                    *reinterpret_cast<float4*>(cp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
                 }
             }
+            __syncwarp();
         }
         tc_fence_before();
     } else if (warp == 4) {
@@ -247,10 +377,15 @@ int tc_supported(const CmganGemmArgs* a) {
     if (a->N % 16 || a->N < 16 || a->N > 256) return 0;
     if (a->Cin % KC) return 0;
     if (a->lda % 4 || ((uintptr_t)a->A & 15)) return 0;
+    if (a->ldc % 4 || ((uintptr_t)a->C & 15)) return 0;
+    if (a->bias && ((uintptr_t)a->bias & 15)) return 0;
     for (int t = 0; t < a->ntaps; ++t)
         if (a->tap_off[t] % 4) return 0;
     if (!a->ws || a->ws_floats < (long long)a->N * a->Cin * a->ntaps) return 0;
     if ((uintptr_t)a->ws & 127) return 0;
+    if (a->pro == CMGAN_PRO_LN && (((uintptr_t)a->p1 & 15) || ((uintptr_t)a->p2 & 15) || a->ntaps != 1)) return 0;
+    if (a->pro == CMGAN_PRO_BN_SWISH && (((uintptr_t)a->p0 & 15) || ((uintptr_t)a->p1 & 15))) return 0;
+    if (a->pro == CMGAN_PRO_IN_PRELU && (((uintptr_t)a->p0 & 15) || ((uintptr_t)a->p1 & 15) || ((uintptr_t)a->p2 & 15) || a->pstride % 4)) return 0;
     return 1;
 }
 
@@ -265,19 +400,23 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     const int nchunks = (a->Cin / KC) * a->ntaps;
-    if (stages > nchunks) stages = nchunks < 2 ? 2 : nchunks;
+    // the epilogue staging (4 warps x 32 rows x 68 floats = 34816 B) lives in the stage memory
+    while ((size_t)stages * (A_STAGE_BYTES + b_stage) < 4 * 32 * STG_LD * sizeof(float)) ++stages;
     int tmem_cols = 32;
     while (tmem_cols < BN) tmem_cols <<= 1;
     const size_t smem = (size_t)stages * (A_STAGE_BYTES + b_stage) + 1024 /*alignment*/ + 8 * (2 * stages + 2) + 16;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
         if (e != cudaSuccess) { cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-        smem_set = 110 * 1024;
+        attr_set = true;
     }
+    (void)nchunks;
     long total = (long)nchunks * BN * KC;
     pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, BN, a->ws);
     if (cmgan_check_launch("pack_b_kernel")) return -1;
-    gemm_rows_tc_kernel<<<cdiv(a->M, BM), NTHREADS, smem, st>>>(*a, a->ws, BN, stages, tmem_cols);
+    if (a->pro == CMGAN_PRO_NONE) gemm_rows_tc_kernel<true><<<cdiv(a->M, BM), NTHREADS, smem, st>>>(*a, a->ws, BN, stages, tmem_cols);
+    else gemm_rows_tc_kernel<false><<<cdiv(a->M, BM), NTHREADS, smem, st>>>(*a, a->ws, BN, stages, tmem_cols);
     return cmgan_check_launch("gemm_rows_tc_kernel");
 }

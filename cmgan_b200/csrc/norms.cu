@@ -219,8 +219,14 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, long ldx, long ro
     long row = i / C;
     long t = (row / rows_per_group) * tstride + c;
     float z = __ldg(x + row * ldx + c) * scale[t] + shift[t];
-    if (act == 1 && z < 0.f) z *= slope[c];
-    else if (act == 2) z = swishf_(z);
+    const int a = act & 15;
+    if (a == 1 && z < 0.f) z *= slope[c];
+    else if (a == 2) z = swishf_(z);
+    if (act & 16) {        // consumer is a tf32 tensor-core GEMM fed by cp.async: round (not truncate) once, here
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(z));
+        z = __uint_as_float(r);
+    }
     y[row * ldy + c] = z;
 }
 

@@ -14,7 +14,7 @@ DEV = "cuda"
 
 if torch.cuda.is_available():
     import cmgan_b200
-    from cmgan_b200 import generator as G, signal
+    from cmgan_b200 import conformer_block as G, signal
     from cmgan_b200.ops import call
 from oracle import cmgan_oracle as O
 from conftest import GOLDEN

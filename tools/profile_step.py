@@ -17,8 +17,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--fwd-only", action="store_true")
+ap.add_argument("--precision", default="tf32")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
+from cmgan_b200 import ops as _ops  # noqa: E402
+_ops.set_precision(args.precision)
 torch.manual_seed(0)
 model = cmgan_b200.TSCNet(64, 201).to(dev).train()
 flat = model.enable_flat_grads()
