@@ -89,4 +89,54 @@ __device__ __forceinline__ float epilogue(const CmganGemmArgs& g, float v, long 
 }
 
 
+// ---- prologue on 4 consecutive k with hoisted per-chunk parameters -----------------------------------
+struct ChunkParams { float4 a, b; };     // LN: gamma, beta;  BN: scale, shift
+
+__device__ __forceinline__ void load_chunk_params(const CmganGemmArgs& g, int k, ChunkParams& cp) {
+    if (g.pro == CMGAN_PRO_LN) { cp.a = __ldg(reinterpret_cast<const float4*>(g.p1 + k)); cp.b = __ldg(reinterpret_cast<const float4*>(g.p2 + k)); }
+    else if (g.pro == CMGAN_PRO_BN_SWISH) { cp.a = __ldg(reinterpret_cast<const float4*>(g.p0 + k)); cp.b = __ldg(reinterpret_cast<const float4*>(g.p1 + k)); }
+}
+
+__device__ __forceinline__ float4 transform4(const CmganGemmArgs& g, float4 v, long r, int k, float mean, float rstd, const ChunkParams& cp) {
+    switch (g.pro) {
+        case CMGAN_PRO_LN:
+            v.x = (v.x - mean) * rstd * cp.a.x + cp.b.x; v.y = (v.y - mean) * rstd * cp.a.y + cp.b.y;
+            v.z = (v.z - mean) * rstd * cp.a.z + cp.b.z; v.w = (v.w - mean) * rstd * cp.a.w + cp.b.w;
+            break;
+        case CMGAN_PRO_BN_SWISH:
+            v.x = swishf_(fmaf(v.x, cp.a.x, cp.b.x)); v.y = swishf_(fmaf(v.y, cp.a.y, cp.b.y));
+            v.z = swishf_(fmaf(v.z, cp.a.z, cp.b.z)); v.w = swishf_(fmaf(v.w, cp.a.w, cp.b.w));
+            break;
+        case CMGAN_PRO_SWISH_DROP: {
+            v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
+            if (g.pro_thr) {
+                uint64_t idx = (uint64_t)r * g.Cin + k;
+                v.x *= cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep); v.y *= cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
+                v.z *= cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep); v.w *= cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
+            }
+            break;
+        }
+        case CMGAN_PRO_DROP: {
+            uint64_t idx = (uint64_t)r * g.Cin + k;
+            v.x *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep);
+            v.y *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
+            v.z *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep);
+            v.w *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
+            break;
+        }
+        case CMGAN_PRO_IN_PRELU: {
+            long b = r / g.rows_per_batch;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.p0 + b * g.pstride + k));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(g.p1 + b * g.pstride + k));
+            const float4 sl = __ldg(reinterpret_cast<const float4*>(g.p2 + k));
+            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            v.x = v.x >= 0.f ? v.x : v.x * sl.x; v.y = v.y >= 0.f ? v.y : v.y * sl.y;
+            v.z = v.z >= 0.f ? v.z : v.z * sl.z; v.w = v.w >= 0.f ? v.w : v.w * sl.w;
+            break;
+        }
+        default: break;
+    }
+    return v;
+}
+
 }  // namespace cmgan_gemm

@@ -183,7 +183,8 @@ int validate(const CmganGemmArgs* a, const char* who) {
 
 }  // namespace
 
-int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st);   // gemm_tc.cu
+int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st);    // gemm_tc.cu
+int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st);   // gemm_wgrad_tc.cu
 
 // C[M, N] = epi(bias + sum_taps pro(A) * B); see gemm_args.h.  Replaces every nn.Linear / nn.Conv1d(k=1) /
 // nn.Conv2d of reference generator.py:24-32,53-63,108 and conformer.py:82-84,140-144,163,173 and their
@@ -208,6 +209,10 @@ CMGAN_API int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream) {
     if (validate(a, "cmgan_gemm_wgrad_f32")) return -1;
     CMGAN_REQUIRE(a->D != nullptr, "cmgan_gemm_wgrad_f32: null D");
     if (a->M == 0) return 0;
+    if (a->precision == 1) {                       // tf32 tcgen05 path (gemm_wgrad_tc.cu); 1 = shape not covered -> exact fp32 path below
+        int rc = cmgan_gemm_wgrad_tc_launch(a, (cudaStream_t)stream);
+        if (rc <= 0) return rc;
+    }
     dim3 grid(cdiv(a->Cin, WK) * a->ntaps, cdiv(a->N, WN), cdiv(a->M, MCH));
     if (vec_ok(*a)) gemm_wgrad_kernel<4><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
     else gemm_wgrad_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);

@@ -20,9 +20,11 @@
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_device.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 using namespace cmgan_gemm;
+using namespace cmgan_tc;
 
 constexpr int BM = 128;              // rows per CTA tile = UMMA M
 constexpr int KC = 32;               // floats per K chunk = one 128-byte swizzle row
@@ -31,87 +33,6 @@ constexpr int NPROD = 128;           // producer / epilogue threads (warps 0-3)
 constexpr int NTHREADS = 192;
 constexpr int SLAB = 64;             // epilogue column slab
 constexpr int STG_LD = SLAB + 4;     // staging row stride (floats): conflict-free 128-bit accesses
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 28)) __trap();        // protocol bug: fail loudly instead of hanging the device
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1): 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address            bits [0,14)
-    d |= (uint64_t)1 << 16;                             // leading byte offset >> 4 bits [16,30) (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset >> 4  bits [32,46)
-    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
-__device__ __forceinline__ uint32_t make_idesc(int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 // ---- weight re-tiling ------------------------------------------------------------------------------
 // out[chunk][n][swizzled 32 floats], chunk = tap * (Cin/32) + kc;  rows n >= N are zero
@@ -127,56 +48,6 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
     if (n < N) v = to_tf32(__ldg(B + (long)tap * sb_tap + (long)(kc * KC + kk) * sb_k + (long)n * sb_n));
     int c = kk >> 2, j = kk & 3;
     out[(chunk * BN + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
-}
-
-// ---- prologue on 4 consecutive k with hoisted per-chunk parameters -----------------------------------
-struct ChunkParams { float4 a, b; };     // LN: gamma, beta;  BN: scale, shift
-
-__device__ __forceinline__ void load_chunk_params(const CmganGemmArgs& g, int k, ChunkParams& cp) {
-    if (g.pro == CMGAN_PRO_LN) { cp.a = __ldg(reinterpret_cast<const float4*>(g.p1 + k)); cp.b = __ldg(reinterpret_cast<const float4*>(g.p2 + k)); }
-    else if (g.pro == CMGAN_PRO_BN_SWISH) { cp.a = __ldg(reinterpret_cast<const float4*>(g.p0 + k)); cp.b = __ldg(reinterpret_cast<const float4*>(g.p1 + k)); }
-}
-
-__device__ __forceinline__ float4 transform4(const CmganGemmArgs& g, float4 v, long r, int k, float mean, float rstd, const ChunkParams& cp) {
-    switch (g.pro) {
-        case CMGAN_PRO_LN:
-            v.x = (v.x - mean) * rstd * cp.a.x + cp.b.x; v.y = (v.y - mean) * rstd * cp.a.y + cp.b.y;
-            v.z = (v.z - mean) * rstd * cp.a.z + cp.b.z; v.w = (v.w - mean) * rstd * cp.a.w + cp.b.w;
-            break;
-        case CMGAN_PRO_BN_SWISH:
-            v.x = swishf_(fmaf(v.x, cp.a.x, cp.b.x)); v.y = swishf_(fmaf(v.y, cp.a.y, cp.b.y));
-            v.z = swishf_(fmaf(v.z, cp.a.z, cp.b.z)); v.w = swishf_(fmaf(v.w, cp.a.w, cp.b.w));
-            break;
-        case CMGAN_PRO_SWISH_DROP: {
-            v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
-            if (g.pro_thr) {
-                uint64_t idx = (uint64_t)r * g.Cin + k;
-                v.x *= cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep); v.y *= cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
-                v.z *= cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep); v.w *= cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
-            }
-            break;
-        }
-        case CMGAN_PRO_DROP: {
-            uint64_t idx = (uint64_t)r * g.Cin + k;
-            v.x *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep);
-            v.y *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
-            v.z *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep);
-            v.w *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
-            break;
-        }
-        case CMGAN_PRO_IN_PRELU: {
-            long b = r / g.rows_per_batch;
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.p0 + b * g.pstride + k));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(g.p1 + b * g.pstride + k));
-            const float4 sl = __ldg(reinterpret_cast<const float4*>(g.p2 + k));
-            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-            v.x = v.x >= 0.f ? v.x : v.x * sl.x; v.y = v.y >= 0.f ? v.y : v.y * sl.y;
-            v.z = v.z >= 0.f ? v.z : v.z * sl.z; v.w = v.w >= 0.f ? v.w : v.w * sl.w;
-            break;
-        }
-        default: break;
-    }
-    return v;
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
@@ -337,14 +208,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_rows_tc_kernel(const __grid_
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BN);
+            const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int s = ch % stages;
                 const uint32_t par = (uint32_t)((ch / stages) & 1);
                 mbar_wait(full_bar(s), par);
                 tc_fence_after();
-                const uint64_t adesc = make_desc(sA + s * A_STAGE_BYTES);
-                const uint64_t bdesc = make_desc(sB + s * b_stage_bytes);
+                const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE_BYTES, 16, 1024);
+                const uint64_t bdesc = make_desc_sw128(sB + s * b_stage_bytes, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < KC / 8; ++k)       // tf32: K = 8 per instruction = 32 bytes along the swizzled row
                     umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ch | k) != 0 ? 1u : 0u);

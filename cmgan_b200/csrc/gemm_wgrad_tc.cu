@@ -1,0 +1,304 @@
+// tf32 tensor-core weight gradient:  dW(tap, k, n) += sum_m pro(A[in_row(m, tap), k]) * prod(D[m, n])   (gemm_args.h, wgrad form)
+//
+// The reduction runs over the rows m, so both MMA operands are "MN-major": a stage holds 32 rows of A (32 x 128 k) and of D
+// (32 x N) exactly as they lie in memory (rows of 128 B pieces), in the canonical MN-major SWIZZLE_128B layout
+//   atom(kb, blk) = 8 rows x 128 B at  blk * LBO + kb * 1024,   16-byte chunk j of row r stored at chunk j ^ r,
+// and tcgen05.mma (kind::tf32, M = 128 = k tile, N, K = 8 rows) accumulates the (128 x N) tile of dW in TMEM over a chunk of
+// rows; the epilogue adds the tile into dW with red.global (the parameter-gradient buffer is zeroed once per step).
+// Grid: (row chunks) x (taps * k tiles).  Warps 0-3 load (cp.async when the operand needs no transform, else registers with the
+// same prologues as the forward GEMM / the dropout scale on D) and later run the epilogue; warp 4 issues the MMAs.
+#include "common.cuh"
+#include "../../include/cmgan_b200.h"
+#include "gemm_device.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace cmgan_gemm;
+using namespace cmgan_tc;
+
+constexpr int RS = 32;               // rows per stage (= 4 MMAs of K = 8)
+constexpr int MO = 128;              // k values per tile = UMMA M
+constexpr int A_STAGE = RS * MO * 4; // 16 KB
+constexpr int NPROD = 128;
+constexpr int NTHREADS = 160;
+constexpr uint32_t BLK = 4096;       // bytes between 32-wide M/N blocks (4 row groups x 1024)
+
+__device__ __forceinline__ void advance_row(const CmganGemmArgs& g, RowInfo& r, int by) {
+    r.x += by;
+    if (g.conv) {
+        while (r.x >= g.OW) { r.x -= g.OW; if (++r.y == g.OH) { r.y = 0; ++r.b; } }
+    }
+}
+
+template <bool A_ASYNC, bool D_ASYNC>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid_constant__ CmganGemmArgs g, int NB, int mch, int stages,
+                                                                     int tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int d_stage = RS * NB * 4;
+    const uint32_t sA = base;
+    const uint32_t sD = base + stages * A_STAGE;
+    const uint32_t bars = sD + stages * d_stage;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (stages + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * stages);
+    const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ktiles = (g.Cin + MO - 1) / MO;
+    const int tap = blockIdx.y / ktiles, k0 = (blockIdx.y % ktiles) * MO;
+    const long mbeg = (long)blockIdx.x * mch;
+    const long mend = mbeg + mch < g.M ? mbeg + mch : g.M;
+    const int nst = (int)((mend - mbeg + RS - 1) / RS);
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), NPROD); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_ptr_addr, (uint32_t)tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp < 4) {
+        // ---------------- producers ----------------
+        // A: thread -> 16-byte chunk j of k block mi, rows rg*8 .. rg*8+7 of the stage
+        const int aj = tid & 7, ami = (tid >> 3) & 3, arg = tid >> 5;
+        const int ak = k0 + ami * 32 + aj * 4;
+        const bool ak_ok = ak < g.Cin;
+        uint32_t a_off[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a_off[i] = ami * BLK + arg * 1024 + i * 128 + ((aj ^ i) << 4);
+        RowInfo r0 = decode_row(g, (int)(mbeg + arg * 8));
+        ChunkParams cp;
+        cp.a = cp.b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!A_ASYNC && ak_ok) load_chunk_params(g, ak, cp);
+        // D: chunks q = tid + 128 u,  u < NB/16
+        const int cpr = NB / 4;
+        const int nd = NB / 16;
+        const int LAG = stages >= 3 ? 2 : 1;
+        constexpr bool ANY_ASYNC = A_ASYNC || D_ASYNC;
+
+        for (int it = 0; it < nst + (ANY_ASYNC ? LAG : 0); ++it) {
+            if (it < nst) {
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                const long mrow = mbeg + (long)it * RS;
+                // ---- gather the 8 A rows of this thread (registers or addresses)
+                long arow[8];
+                {
+                    RowInfo r = r0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long m = mrow + arg * 8 + i;
+                        r.ok = m < mend;
+                        arow[i] = in_row_of(g, r, tap);
+                        advance_row(g, r, 1);
+                    }
+                    advance_row(g, r0, RS);
+                }
+                float4 av[8];
+                if (!A_ASYNC) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (arow[i] >= 0 && ak_ok) {
+                            av[i] = __ldg(reinterpret_cast<const float4*>(g.A + g.tap_off[tap] + arow[i] * g.lda + ak));
+                            float mean = 0.f, rstd = 1.f;
+                            if (g.pro == CMGAN_PRO_LN) { float2 st = __ldg(reinterpret_cast<const float2*>(g.p0) + arow[i]); mean = st.x; rstd = st.y; }
+                            av[i] = transform4(g, av[i], arow[i], ak, mean, rstd, cp);
+                        }
+                    }
+                }
+                float4 dv[16];
+                if (!D_ASYNC) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (u < nd) {
+                            const int q = tid + 128 * u;
+                            const int row = q / cpr, cc = q % cpr;
+                            const long m = mrow + row;
+                            dv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (m < mend) {
+                                dv[u] = __ldg(reinterpret_cast<const float4*>(g.D + m * g.ldd + cc * 4));
+                                if (g.prod == 1) {
+                                    uint64_t idx = (uint64_t)m * g.N + cc * 4;
+                                    dv[u].x *= g.alpha * cmgan_drop_scale(g.seed, idx, g.drop_thr, g.inv_keep);
+                                    dv[u].y *= g.alpha * cmgan_drop_scale(g.seed, idx + 1, g.drop_thr, g.inv_keep);
+                                    dv[u].z *= g.alpha * cmgan_drop_scale(g.seed, idx + 2, g.drop_thr, g.inv_keep);
+                                    dv[u].w *= g.alpha * cmgan_drop_scale(g.seed, idx + 3, g.drop_thr, g.inv_keep);
+                                }
+                            }
+                        }
+                    }
+                }
+                mbar_wait(empty_bar(s), par ^ 1u);
+                const uint32_t abase = sA + s * A_STAGE, dbase = sD + s * d_stage;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (A_ASYNC) {
+                        const bool ok = arow[i] >= 0 && ak_ok;
+                        cp_async16(abase + a_off[i], g.A + (ok ? g.tap_off[tap] + arow[i] * g.lda + ak : 0), ok ? 16u : 0u);
+                    } else {
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(abase + a_off[i]), "f"(to_tf32(av[i].x)), "f"(to_tf32(av[i].y)),
+                                     "f"(to_tf32(av[i].z)), "f"(to_tf32(av[i].w)) : "memory");
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    if (u < nd) {
+                        const int q = tid + 128 * u;
+                        const int row = q / cpr, cc = q % cpr;
+                        const uint32_t off = (uint32_t)(cc >> 3) * BLK + (row >> 3) * 1024 + (row & 7) * 128 + (((cc & 7) ^ (row & 7)) << 4);
+                        if (D_ASYNC) {
+                            const long m = mrow + row;
+                            const bool ok = m < mend;
+                            cp_async16(dbase + off, g.D + (ok ? m * g.ldd + cc * 4 : 0), ok ? 16u : 0u);
+                        } else {
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dbase + off), "f"(to_tf32(dv[u].x)), "f"(to_tf32(dv[u].y)),
+                                         "f"(to_tf32(dv[u].z)), "f"(to_tf32(dv[u].w)) : "memory");
+                        }
+                    }
+                }
+                if (!ANY_ASYNC) { fence_proxy_async(); mbar_arrive(full_bar(s)); }
+            }
+            if (ANY_ASYNC) {
+                cp_async_commit();
+                const int done = it - LAG;
+                if (done >= 0) {
+                    if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                    fence_proxy_async();
+                    mbar_arrive(full_bar(done % stages));
+                }
+            }
+        }
+        // ---------------- epilogue: dW tile += accumulator ----------------
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int k = k0 + warp * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int n0 = 0; n0 < NB; n0 += 16) {
+            float acc[16];
+            tmem_ld16(trow + (uint32_t)n0, acc);
+            if (k < g.Cin) {
+                float* dst = g.C + (long)tap * g.sb_tap + (long)k * g.sb_k;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < g.N) atomicAdd(dst + (long)(n0 + j) * g.sb_n, acc[j]);
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(MO, NB, 1, 1);
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                mbar_wait(full_bar(s), par);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < RS / 8; ++kb) {
+                    const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE + kb * 1024, BLK, 1024);
+                    const uint64_t ddesc = make_desc_sw128(sD + s * d_stage + kb * 1024, BLK, 1024);
+                    umma_tf32(tmem_base, adesc, ddesc, idesc, (it | kb) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    }
+}
+
+// dbias[n] += sum_m prod(D[m, n])
+__global__ void colsum_kernel(const float* __restrict__ D, long ldd, long M, int N, int prod, float alpha, unsigned long long seed, unsigned thr,
+                              float inv_keep, int rows_per_block, float* __restrict__ out) {
+    __shared__ float sm[256];
+    const int c = threadIdx.x % N, rg = threadIdx.x / N, nrg = blockDim.x / N;
+    const long r_beg = (long)blockIdx.x * rows_per_block;
+    const long r_end = r_beg + rows_per_block < M ? r_beg + rows_per_block : M;
+    float s = 0.f;
+    if (rg < nrg)
+        for (long m = r_beg + rg; m < r_end; m += nrg) {
+            float d = __ldg(D + m * ldd + c);
+            if (prod == 1) d *= alpha * cmgan_drop_scale(seed, (uint64_t)m * N + c, thr, inv_keep);
+            s += d;
+        }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float t = 0.f;
+        for (int q = 0; q < nrg; ++q) t += sm[q * N + c];
+        atomicAdd(out + c, t);
+    }
+}
+
+int wgrad_tc_supported(const CmganGemmArgs* a) {
+    if (a->N % 32 || a->N < 32 || a->N > 256) return 0;
+    if (a->Cin % 4) return 0;
+    if (a->lda % 4 || ((uintptr_t)a->A & 15) || a->ldd % 4 || ((uintptr_t)a->D & 15)) return 0;
+    for (int t = 0; t < a->ntaps; ++t)
+        if (a->tap_off[t] % 4) return 0;
+    if (a->pro == CMGAN_PRO_LN && (((uintptr_t)a->p1 & 15) || ((uintptr_t)a->p2 & 15))) return 0;
+    if (a->pro == CMGAN_PRO_BN_SWISH && (((uintptr_t)a->p0 & 15) || ((uintptr_t)a->p1 & 15))) return 0;
+    if (a->pro == CMGAN_PRO_IN_PRELU) return 0;
+    return 1;
+}
+
+template <bool AA, bool DA>
+int launch(const CmganGemmArgs* a, dim3 grid, size_t smem, int NB, int mch, int stages, int tmem_cols, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_tc_kernel<AA, DA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+        if (e != cudaSuccess) { cmgan_set_error("gemm_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+        attr_set = true;
+    }
+    gemm_wgrad_tc_kernel<AA, DA><<<grid, NTHREADS, smem, st>>>(*a, NB, mch, stages, tmem_cols);
+    return cmgan_check_launch("gemm_wgrad_tc_kernel");
+}
+
+}  // namespace
+
+// tf32 tensor-core path of cmgan_gemm_wgrad (same contract).  Returns 1 if the shape is not covered (caller falls back).
+int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
+    if (!wgrad_tc_supported(a)) return 1;
+    const int NB = a->N;
+    const int d_stage = RS * NB * 4;
+    int stages = (100 * 1024 - 2048) / (A_STAGE + d_stage);
+    if (stages > 4) stages = 4;
+    if (stages < 2) stages = 2;
+    int tmem_cols = 32;
+    while (tmem_cols < NB) tmem_cols <<= 1;
+    const int ktiles = (a->Cin + MO - 1) / MO;
+    const int ytiles = ktiles * a->ntaps;
+    // rows per CTA: enough CTAs for ~3 waves of 296 resident CTAs, at least 16 stages per CTA to amortise the TMEM round trip
+    long want = 888 / ytiles;
+    if (want < 1) want = 1;
+    long mch = (a->M + want - 1) / want;
+    mch = ((mch + RS - 1) / RS) * RS;
+    if (mch < 16 * RS) mch = 16 * RS;
+    dim3 grid((unsigned)((a->M + mch - 1) / mch), (unsigned)ytiles);
+    const size_t smem = (size_t)stages * (A_STAGE + d_stage) + 1024 + 8 * (2 * stages + 2) + 16;
+    const bool aa = a->pro == CMGAN_PRO_NONE, da = a->prod == 0;
+    int rc;
+    if (aa && da) rc = launch<true, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
+    else if (aa) rc = launch<true, false>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
+    else if (da) rc = launch<false, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
+    else rc = launch<false, false>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
+    if (rc) return rc;
+    if (a->dbias) {
+        const int rpb = 2048;
+        colsum_kernel<<<cdiv(a->M, rpb), 256, 0, st>>>(a->D, a->ldd, a->M, a->N, a->prod, a->alpha, a->seed, a->drop_thr, a->inv_keep, rpb, a->dbias);
+        return cmgan_check_launch("colsum_kernel");
+    }
+    return 0;
+}

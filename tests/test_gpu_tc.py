@@ -115,3 +115,83 @@ def test_tc_end_to_end_waveform(g_weights):
     snr = 10 * np.log10((ref ** 2).sum().item() / ((e - ref) ** 2).sum().item())
     print(f"[parity-tf32] p232_170 (2.09 s real speech): waveform max-abs {err:.3e}, SNR vs reference output {snr:.1f} dB")
     assert err <= 1e-3
+
+
+def _both_wgrad(name, w_shape, nbias, tol=4e-3, **kw):
+    outs = []
+    for prec in (0, 1):
+        dw = torch.zeros(*w_shape, device=DEV)
+        db = torch.zeros(nbias, device=DEV)
+        gemm(wgrad=True, W=None, C=dw, ldc=0, dbias=db, precision=prec, **kw)
+        torch.cuda.synchronize()
+        outs.append((dw, db))
+    for what, i in (("dW", 0), ("dbias", 1)):
+        ref, got = outs[0][i].double(), outs[1][i].double()
+        err = (got - ref).abs().max().item()
+        den = ref.abs().max().item()
+        print(f"[parity-tf32] {name} {what}: max-abs {err:.3e} (range {den:.3e}, rel {err / max(den, 1e-30):.3e})")
+        assert np.isfinite(err) and err <= tol * max(den, 1e-6), f"{name} {what}"
+    assert not torch.equal(outs[0][0], outs[1][0]), f"{name}: tf32 wgrad returned bit-identical results (did it run?)"
+
+
+@pytest.mark.parametrize("M,N,K", [(3000, 64, 64), (5000, 256, 64), (2600, 64, 256), (999, 128, 128), (70, 64, 64)])
+def test_tc_wgrad_linear(M, N, K):
+    A, D = _rand(M, K, seed=31), _rand(M, N, seed=32)
+    _both_wgrad(f"wgrad linear {M}x{N}x{K}", (N, K), N, A=A, lda=K, Cin=K, D=D, ldd=N, N=N, sb_k=1, sb_n=K, M=M)
+
+
+@pytest.mark.parametrize("dil,Cin", [(1, 64), (4, 192), (8, 256)])
+def test_tc_wgrad_conv(dil, Cin):
+    B, T, Fw = 2, 19, 23
+    M = B * T * Fw
+    x, dy = _rand(M, 320, seed=33), _rand(M, 64, seed=34)
+    taps = [((kh - 1) * dil, kw - 1) for kh in range(2) for kw in range(3)]
+    c0 = 320 - Cin
+    _both_wgrad(f"wgrad dilated conv dil={dil} Cin={Cin}", (64, Cin, 2, 3), 64, A=(x, c0), lda=320, Cin=Cin, taps=taps,
+                conv=dict(OH=T, OW=Fw, IH=T, IW=Fw), D=dy, ldd=64, N=64, sb_tap=1, sb_k=6, sb_n=Cin * 6, M=M)
+
+
+def test_tc_wgrad_prologues():
+    M, K, N = 2000, 64, 256
+    x, dh = _rand(M, K, seed=35), _rand(M, N, seed=36)
+    g, be = _rand(K, seed=37), _rand(K, seed=38)
+    st = torch.empty(M, 2, device=DEV)
+    call("cmgan_ln_stats", x, K, M, st)
+    _both_wgrad("wgrad LN prologue", (N, K), N, A=x, lda=K, Cin=K, pro=ops.PRO_LN, p0=st, p1=g, p2=be, D=dh, ldd=N, N=N, sb_k=1, sb_n=K, M=M)
+    h, dx = _rand(M, N, seed=39), _rand(M, K, seed=40)
+    _both_wgrad("wgrad swish+dropout prologue, dropout on D", (K, N), K, A=h, lda=N, Cin=N, pro=ops.PRO_SWISH_DROP, pro_seed=11, pro_drop_p=0.2,
+                D=dx, ldd=K, N=K, prod=1, alpha=0.5, seed=12, drop_p=0.2, sb_k=1, sb_n=N, M=M)
+    d = _rand(M, 128, seed=41)
+    sc, sh = _rand(128, seed=42).abs() + 0.5, _rand(128, seed=43)
+    _both_wgrad("wgrad BN-swish prologue", (K, 128), K, A=d, lda=128, Cin=128, pro=ops.PRO_BN_SWISH, p0=sc, p1=sh, D=dx, ldd=K, N=K, sb_k=1,
+                sb_n=128, M=M)
+    dq = _rand(M, 192, seed=44)
+    _both_wgrad("wgrad strided D (qkv slice)", (128, K), 128, A=x, lda=K, Cin=K, pro=ops.PRO_LN, p0=st, p1=g, p2=be, D=(dq, 64), ldd=192, N=128,
+                sb_k=1, sb_n=K, M=M)
+
+
+def test_tc_training_gradients(g_weights, golden):
+    """whole-network gradients in tf32 mode vs the fp32 FFMA path (same kernels otherwise)"""
+    import torch.nn.functional as F
+    x = torch.from_numpy(golden["compress"]).permute(0, 1, 3, 2)[:, :, :21].contiguous().to(DEV)
+    grads = []
+    for mode in ("fp32", "tf32"):
+        ops.set_precision(mode)
+        try:
+            m = cmgan_b200.TSCNet(64, 201)
+            m.load_state_dict(g_weights, strict=True)
+            m = m.to(DEV).eval()
+            fr, fi = m(x)
+            (fr.square().mean() + fi.abs().mean()).backward()
+            grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
+        finally:
+            ops.set_precision("fp32")
+    gmax = max(v.abs().max().item() for v in grads[0].values())
+    worst, wk = 0.0, ""
+    for k in grads[0]:
+        ref = grads[0][k]
+        e = (grads[1][k] - ref).abs().max().item() / max(ref.abs().max().item(), 1e-3 * gmax)
+        if e > worst:
+            worst, wk = e, k
+    print(f"[parity-tf32] worst relative parameter-gradient deviation tf32 vs fp32: {worst:.3e} at {wk}")
+    assert worst < 3e-2
