@@ -272,6 +272,9 @@ def run_ours(args):
     step(clean, noisy)
     torch.cuda.synchronize()
     probe, ops.PROBE = ops.PROBE, None
+    if os.environ.get("CMGAN_PROBE_DUMP") and rank == 0:      # per-launch GEMM timings for analysis (not part of the JSON line)
+        with open(os.environ["CMGAN_PROBE_DUMP"], "w") as fh:
+            json.dump([[n, M, N, K, e0.elapsed_time(e1) * 1e3] for n, M, N, K, e0, e1 in probe], fh)
     t_rows = sum(e0.elapsed_time(e1) for n, M, N, K, e0, e1 in probe if n == "cmgan_gemm_rows_f32") * 1e-3
     f_rows = sum(2.0 * M * N * K for n, M, N, K, e0, e1 in probe if n == "cmgan_gemm_rows_f32")
     t_wg = sum(e0.elapsed_time(e1) for n, M, N, K, e0, e1 in probe if n == "cmgan_gemm_wgrad_f32") * 1e-3

@@ -377,7 +377,7 @@ CMGAN_API int cmgan_attention_bwd(const float* qkv, const float* E, const float*
     if (cmgan_check_launch("attn_bwd_dq_kernel")) return -1;
     attn_bwd_dkv_kernel<<<grid, NTH, 0, st>>>(qkv, g, E, dctx, lse, delta, dqkv);
     if (cmgan_check_launch("attn_bwd_dkv_kernel")) return -1;
-    const int spb = 8;
+    const int spb = 1;      // one sequence (x 4 heads) per block: enough blocks to fill the GPU; 16 red.global per thread at the end
     dim3 gridE(cdiv(g.n_seq, spb), cdiv(2 * g.L - 1, NTH));
     attn_bwd_dE_kernel<<<gridE, NTH, 0, st>>>(qkv, g, E, dctx, lse, delta, spb, dE);
     return cmgan_check_launch("attn_bwd_dE_kernel");

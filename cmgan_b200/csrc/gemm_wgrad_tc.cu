@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
         const bool ak_ok = ak < g.Cin;
         uint32_t a_off[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a_off[i] = ami * BLK + arg * 1024 + i * 128 + ((aj ^ i) << 4);
+        for (int i = 0; i < 8; ++i) a_off[i] = ami * BLK + arg * 1024 + i * 128 + ((((aj >> 1) ^ (i & 3)) << 5) | ((aj & 1) << 4));
         RowInfo r0 = decode_row(g, (int)(mbeg + arg * 8));
         ChunkParams cp;
         cp.a = cp.b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                     if (u < nd) {
                         const int q = tid + 128 * u;
                         const int row = q / cpr, cc = q % cpr;
-                        const uint32_t off = (uint32_t)(cc >> 3) * BLK + (row >> 3) * 1024 + (row & 7) * 128 + (((cc & 7) ^ (row & 7)) << 4);
+                        const uint32_t off = (uint32_t)(cc >> 3) * BLK + row * 128 + (((((cc & 7) >> 1) ^ (row & 3)) << 5) | ((cc & 1) << 4));
                         if (D_ASYNC) {
                             const long m = mrow + row;
                             const bool ok = m < mend;
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                 tc_fence_after();
 #pragma unroll
                 for (int kb = 0; kb < RS / 8; ++kb) {
-                    const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE + kb * 1024, BLK, 1024);
-                    const uint64_t ddesc = make_desc_sw128(sD + s * d_stage + kb * 1024, BLK, 1024);
+                    const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE + kb * 1024, BLK, 512, 1);
+                    const uint64_t ddesc = make_desc_sw128(sD + s * d_stage + kb * 1024, BLK, 512, 1);
                     umma_tf32(tmem_base, adesc, ddesc, idesc, (it | kb) != 0 ? 1u : 0u);
                 }
                 umma_commit(empty_bar(s));

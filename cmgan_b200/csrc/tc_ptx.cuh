@@ -74,13 +74,13 @@ __device__ __forceinline__ float to_tf32(float x) {
 //   K-major operand  (rows = M/N index, 128 B = 32 tf32 along K): lbo unused (1), sbo = 1024 (next 8-row group)
 //   MN-major operand (rows = K index, 128 B = 32 tf32 along M/N):  lbo = byte distance between 32-wide M/N blocks,
 //                                                                  sbo = byte distance between 8-row K groups
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address            bits [0,14)
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset >> 4 bits [16,30)
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride byte offset >> 4  bits [32,46)
     d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;                   // 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks)
     return d;
 }
 // cute::UMMA::InstrDescriptor for kind::tf32 with fp32 accumulation; a_mn / b_mn = 1 for MN-major operands

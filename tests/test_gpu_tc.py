@@ -182,7 +182,7 @@ def test_tc_training_gradients(g_weights, golden):
             m.load_state_dict(g_weights, strict=True)
             m = m.to(DEV).eval()
             fr, fi = m(x)
-            (fr.square().mean() + fi.abs().mean()).backward()
+            (fr.square().mean() + fi.square().mean()).backward()      # smooth loss: no sign flips between the two precisions
             grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
         finally:
             ops.set_precision("fp32")
