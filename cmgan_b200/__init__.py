@@ -6,7 +6,8 @@ The compute is libcmgan_b200.so (hand-written CUDA, C ABI in include/cmgan_b200.
 PyTorch-op fallback: importing works anywhere, running requires the built library and a CUDA device.
 """
 from .generator import TSCNet  # noqa: F401
+from .discriminator import Discriminator  # noqa: F401
 from .utils import power_compress, power_uncompress  # noqa: F401
 from . import signal  # noqa: F401
 
-__all__ = ["TSCNet", "power_compress", "power_uncompress", "signal"]
+__all__ = ["TSCNet", "Discriminator", "power_compress", "power_uncompress", "signal"]

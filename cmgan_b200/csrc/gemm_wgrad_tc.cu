@@ -296,7 +296,7 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     else rc = launch<false, false>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     if (rc) return rc;
     if (a->dbias) {
-        const int rpb = 2048;
+        const int rpb = 64 * (256 / a->N > 0 ? 256 / a->N : 1);     // ~64 rows per thread -> thousands of blocks
         colsum_kernel<<<cdiv(a->M, rpb), 256, 0, st>>>(a->D, a->ldd, a->M, a->N, a->prod, a->alpha, a->seed, a->drop_thr, a->inv_keep, rpb, a->dbias);
         return cmgan_check_launch("colsum_kernel");
     }
