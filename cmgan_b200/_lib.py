@@ -38,6 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("D", ctypes.c_void_p), ("ldd", ctypes.c_longlong), ("prod", ctypes.c_int), ("dbias", ctypes.c_void_p),
         ("precision", ctypes.c_int),
         ("ws", ctypes.c_void_p), ("ws_floats", ctypes.c_longlong),
+        ("C2", ctypes.c_void_p), ("ldc2", ctypes.c_longlong),
     ]
 
 

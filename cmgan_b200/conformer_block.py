@@ -3,19 +3,19 @@ kernels: forward and hand-written backward orchestration (ref: conformer.py:182-
 
 Rows are channel-last (b, t, f) x 64; a block processes either all time sequences (axis 0) or all frequency sequences
 (axis 1) of the (B, T, F2) grid without ever transposing: only the attention and depthwise-convolution kernels look at
-the sequence axis.  Helper classes for normalisation tables / statistics scratch live here too.
+the sequence axis.  Every GEMM operand that needs a non-linearity in front of it is materialised once by the kernel that
+produces it (LayerNorm output, Swish(+dropout) of the feed-forward hidden layer via the dual-output GEMM epilogue,
+BatchNorm+Swish of the depthwise output), so the tensor-core GEMMs stream their A operand with plain async copies.
+Helper classes for normalisation tables / statistics scratch live here too.
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
-import torch.nn as nn
 
 from . import ops
-from .ops import (EPI_ACC, EPI_DBNSWISH, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_NONE, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU, PRO_LN,
-                  PRO_SWISH_DROP, call, gemm)
+from .ops import EPI_ACC, EPI_DBNSWISH, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_SWISH_DUAL, PRO_DROP, call, gemm
 
 C = 64          # num_channel (the kernels are specialised for 64 channels = 4 heads x 16)
 CAT = 5 * C     # width of a dense-block concat buffer: [out4 | out3 | out2 | out1 | x]
@@ -28,8 +28,7 @@ def _empty(*shape, dev, dtype=torch.float32):
 
 
 class _Tabs:
-    """scale/shift/mean/rstd per (group, channel) and PReLU slope per channel of a normalisation site
-    (or of all five 64-channel slots of a dense-block concat buffer)."""
+    """scale/shift/mean/rstd per (group, channel) and PReLU slope per channel of a normalisation site"""
 
     def __init__(self, G, width, dev, identity=False):
         self.scale = _empty(G, width, dev=dev)
@@ -38,7 +37,7 @@ class _Tabs:
         self.rstd = _empty(G, width, dev=dev)
         self.slope = _empty(width, dev=dev)
         self.width = width
-        if identity:    # slot 4 of a decoder concat buffer holds final activations: act(x) = x
+        if identity:
             call("cmgan_fill", self.scale, G * width, 1.0)
             call("cmgan_fill", self.shift, G * width, 0.0)
             call("cmgan_fill", self.slope, width, 1.0)
@@ -79,6 +78,11 @@ def _site_seed(seed: int, block_id: int, site: int) -> int:
     return (seed * 1000003 + block_id * 16 + site + 1) & 0xFFFFFFFFFFFFFFFF
 
 
+def _rnd() -> int:
+    """1 when the GEMM consumers run on the tf32 tensor cores (round materialised operands once, to nearest)"""
+    return 1 if ops.PRECISION == 1 else 0
+
+
 # ====================================================================================== conformer block
 def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums, save: Optional[dict]):
     """ConformerBlock + the outer TSCB residual (ref: conformer.py:216-222, generator.py:95,97).
@@ -88,27 +92,32 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
     dp = FF_DROP if training else 0.0
     da = ATT_DROP if training else 0.0
     sd = [_site_seed(seed, block_id, i) for i in range(5)]
+    keep = save is not None
+
+    def layer_norm(xin, wkey, bkey):
+        st = _empty(M, 2, dev=dev)
+        xn = _empty(M, C, dev=dev)
+        call("cmgan_ln_apply", xin, C, M, P[wkey], P[bkey], None, 0, xn, C, st, _rnd())
+        return xn, st
 
     def ff(xin, name, s1, s2):
-        st = _empty(M, 2, dev=dev)
-        call("cmgan_ln_stats", xin, C, M, st)
-        h = _empty(M, 4 * C, dev=dev)
-        gemm(A=xin, lda=C, W=P[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.{name}.fn.fn.net.0.bias"], C=h, ldc=4 * C, M=M,
-             N=4 * C, Cin=C, pro=PRO_LN, p0=st, p1=P[f"{p}.{name}.fn.norm.weight"], p2=P[f"{p}.{name}.fn.norm.bias"])
+        """0.5 * FF(LN(x)) + x  (ref: conformer.py:54-72,136-148,211-212)"""
+        xn, st = layer_norm(xin, f"{p}.{name}.fn.norm.weight", f"{p}.{name}.fn.norm.bias")
+        h = _empty(M, 4 * C, dev=dev) if keep else None          # pre-activation: only the backward pass needs it
+        a = _empty(M, 4 * C, dev=dev)                            # swish(h) * dropout: operand of the second Linear
+        gemm(A=xn, lda=C, W=P[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.{name}.fn.fn.net.0.bias"], C=h, ldc=4 * C, M=M,
+             N=4 * C, Cin=C, epi=EPI_SWISH_DUAL, C2=a, ldc2=4 * C, seed=s1, drop_p=dp)
         out = _empty(M, C, dev=dev)
-        gemm(A=h, lda=4 * C, W=P[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, bias=P[f"{p}.{name}.fn.fn.net.3.bias"], C=out, ldc=C, M=M,
-             N=C, Cin=4 * C, pro=PRO_SWISH_DROP, pro_seed=s1, pro_drop_p=dp, epi=EPI_DROP_RES, alpha=0.5, R=xin, ldr=C, seed=s2, drop_p=dp)
-        return st, h, out
+        gemm(A=a, lda=4 * C, W=P[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, bias=P[f"{p}.{name}.fn.fn.net.3.bias"], C=out, ldc=C, M=M,
+             N=C, Cin=4 * C, epi=EPI_DROP_RES, alpha=0.5, R=xin, ldr=C, seed=s2, drop_p=dp)
+        return dict(xn=xn, st=st, h=h, a=a), out
 
-    st1, h1, x1 = ff(x, "ff1", sd[0], sd[1])
+    f1, x1 = ff(x, "ff1", sd[0], sd[1])
     # ---- attention (ref: conformer.py:90-133)
-    st2 = _empty(M, 2, dev=dev)
-    call("cmgan_ln_stats", x1, C, M, st2)
+    xn2, st2 = layer_norm(x1, f"{p}.attn.norm.weight", f"{p}.attn.norm.bias")
     qkv = _empty(M, 3 * C, dev=dev)
-    lnw, lnb = P[f"{p}.attn.norm.weight"], P[f"{p}.attn.norm.bias"]
-    gemm(A=x1, lda=C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, C=qkv, ldc=3 * C, M=M, N=C, Cin=C, pro=PRO_LN, p0=st2, p1=lnw, p2=lnb)
-    gemm(A=x1, lda=C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, C=(qkv, C), ldc=3 * C, M=M, N=2 * C, Cin=C, pro=PRO_LN, p0=st2, p1=lnw,
-         p2=lnb)
+    gemm(A=xn2, lda=C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, C=qkv, ldc=3 * C, M=M, N=C, Cin=C)
+    gemm(A=xn2, lda=C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, C=(qkv, C), ldc=3 * C, M=M, N=2 * C, Cin=C)
     ctx = _empty(M, C, dev=dev)
     lse = _empty(M, 4, dev=dev)
     call("cmgan_attention_fwd", qkv, P[f"{p}.attn.fn.rel_pos_emb.weight"], B, T, F2, axis, ctx, lse)
@@ -116,11 +125,9 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
     gemm(A=ctx, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.attn.fn.to_out.bias"], C=x2, ldc=C, M=M, N=C, Cin=C,
          epi=EPI_DROP_RES, alpha=1.0, R=x1, ldr=C, seed=sd[2], drop_p=da)
     # ---- convolution module (ref: conformer.py:160-173)
-    st3 = _empty(M, 2, dev=dev)
-    call("cmgan_ln_stats", x2, C, M, st3)
+    xn3, st3 = layer_norm(x2, f"{p}.conv.net.0.weight", f"{p}.conv.net.0.bias")
     g = _empty(M, 4 * C, dev=dev)
-    gemm(A=x2, lda=C, W=P[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.conv.net.2.bias"], C=g, ldc=4 * C, M=M, N=4 * C, Cin=C,
-         pro=PRO_LN, p0=st3, p1=P[f"{p}.conv.net.0.weight"], p2=P[f"{p}.conv.net.0.bias"])
+    gemm(A=xn3, lda=C, W=P[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.conv.net.2.bias"], C=g, ldc=4 * C, M=M, N=4 * C, Cin=C)
     d = _empty(M, 2 * C, dev=dev)
     call("cmgan_glu_dwconv_fwd", g, P[f"{p}.conv.net.4.conv.weight"], P[f"{p}.conv.net.4.conv.bias"], B, T, F2, axis, d)
     bn = _Tabs(1, 2 * C, dev)
@@ -131,17 +138,19 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
         call("cmgan_norm_finalize", s, M, 1, 2 * C, 0, *bnp, 0.1, bn.scale, bn.shift, bn.mean, bn.rstd, 2 * C)
     else:
         call("cmgan_norm_finalize", None, M, 1, 2 * C, 1, *bnp, 0.1, bn.scale, bn.shift, bn.mean, bn.rstd, 2 * C)
+    dsw = _empty(M, 2 * C, dev=dev)           # swish(bn(d)): operand of the second pointwise conv
+    call("cmgan_norm_apply", d, 2 * C, 1, M, 2 * C, 2 | (16 * _rnd()), bn.scale, bn.shift, 2 * C, None, dsw, 2 * C)
     x3 = _empty(M, C, dev=dev)
-    gemm(A=d, lda=2 * C, W=P[f"{p}.conv.net.7.weight"], sb_k=1, sb_n=2 * C, bias=P[f"{p}.conv.net.7.bias"], C=x3, ldc=C, M=M, N=C, Cin=2 * C,
-         pro=PRO_BN_SWISH, p0=bn.scale, p1=bn.shift, epi=EPI_DROP_RES, alpha=1.0, R=x2, ldr=C)
+    gemm(A=dsw, lda=2 * C, W=P[f"{p}.conv.net.7.weight"], sb_k=1, sb_n=2 * C, bias=P[f"{p}.conv.net.7.bias"], C=x3, ldc=C, M=M, N=C, Cin=2 * C,
+         epi=EPI_DROP_RES, alpha=1.0, R=x2, ldr=C)
     # ---- second feed-forward, post norm, outer residual
-    st4, h2, x4 = ff(x3, "ff2", sd[3], sd[4])
+    f2, x4 = ff(x3, "ff2", sd[3], sd[4])
     st5 = _empty(M, 2, dev=dev)
     y = _empty(M, C, dev=dev)
-    call("cmgan_ln_apply", x4, C, M, P[f"{p}.post_norm.weight"], P[f"{p}.post_norm.bias"], x, C, y, C, st5)
+    call("cmgan_ln_apply", x4, C, M, P[f"{p}.post_norm.weight"], P[f"{p}.post_norm.bias"], x, C, y, C, st5, 0)
     if save is not None:
-        save.update(x=x, st1=st1, h1=h1, x1=x1, st2=st2, qkv=qkv, ctx=ctx, lse=lse, x2=x2, st3=st3, g=g, d=d, bn=bn, x3=x3, st4=st4, h2=h2,
-                    x4=x4, st5=st5, sd=sd, dp=dp, da=da, axis=axis, training=training, p=p)
+        save.update(x=x, f1=f1, x1=x1, xn2=xn2, st2=st2, qkv=qkv, ctx=ctx, lse=lse, x2=x2, xn3=xn3, st3=st3, g=g, d=d, dsw=dsw, bn=bn, x3=x3,
+                    f2=f2, x4=x4, st5=st5, sd=sd, dp=dp, da=da, axis=axis, training=training, p=p)
     return y
 
 
@@ -151,35 +160,35 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     M = dy.shape[0]
     p, axis, dp, da, sd = S["p"], S["axis"], S["dp"], S["da"], S["sd"]
 
-    def ff_bwd(dout, xin, st, h, name, s1, s2, res2=None):
-        # out = xin + 0.5 * drop2(W2 (swish(h) * drop1) + b2),  h = W1 LN(xin) + b1
+    def ff_bwd(dout, xin, f, name, s1, s2, res2=None):
+        # out = xin + 0.5 * drop2(W2 a + b2),  a = swish(h) * drop1,  h = W1 LN(xin) + b1
         W1, W2 = P[f"{p}.{name}.fn.fn.net.0.weight"], P[f"{p}.{name}.fn.fn.net.3.weight"]
         dh = _empty(M, 4 * C, dev=dev)
         gemm(A=dout, lda=C, W=W2, sb_k=4 * C, sb_n=1, C=dh, ldc=4 * C, M=M, N=4 * C, Cin=C, pro=PRO_DROP, pro_alpha=0.5, pro_seed=s2,
-             pro_drop_p=dp, epi=EPI_DSWISH_DROP, aux=h, ldaux=4 * C, seed=s1, drop_p=dp)
-        gemm(wgrad=True, A=h, lda=4 * C, Cin=4 * C, pro=PRO_SWISH_DROP, pro_seed=s1, pro_drop_p=dp, D=dout, ldd=C, N=C, prod=1, alpha=0.5, seed=s2,
-             drop_p=dp, W=None, C=G[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.3.bias"])
+             pro_drop_p=dp, epi=EPI_DSWISH_DROP, aux=f["h"], ldaux=4 * C, seed=s1, drop_p=dp)
+        gemm(wgrad=True, A=f["a"], lda=4 * C, Cin=4 * C, D=dout, ldd=C, N=C, prod=1, alpha=0.5, seed=s2, drop_p=dp, W=None,
+             C=G[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.3.bias"])
         dln = _empty(M, C, dev=dev)
         gemm(A=dh, lda=4 * C, W=W1, sb_k=C, sb_n=1, C=dln, ldc=C, M=M, N=C, Cin=4 * C)
-        gemm(wgrad=True, A=xin, lda=C, Cin=C, pro=PRO_LN, p0=st, p1=P[f"{p}.{name}.fn.norm.weight"], p2=P[f"{p}.{name}.fn.norm.bias"], D=dh,
-             ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.0.bias"])
+        gemm(wgrad=True, A=f["xn"], lda=C, Cin=C, D=dh, ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, ldc=0,
+             M=M, dbias=G[f"{p}.{name}.fn.fn.net.0.bias"])
         dxin = _empty(M, C, dev=dev)
-        call("cmgan_ln_bwd", dln, C, xin, C, st, P[f"{p}.{name}.fn.norm.weight"], M, dout, C, res2, C, dxin, C, G[f"{p}.{name}.fn.norm.weight"],
-             G[f"{p}.{name}.fn.norm.bias"])
+        call("cmgan_ln_bwd", dln, C, xin, C, f["st"], P[f"{p}.{name}.fn.norm.weight"], M, dout, C, res2, C, dxin, C,
+             G[f"{p}.{name}.fn.norm.weight"], G[f"{p}.{name}.fn.norm.bias"])
         return dxin
 
     # y = LN(x4) * g + b + x
     dx4 = _empty(M, C, dev=dev)
     call("cmgan_ln_bwd", dy, C, S["x4"], C, S["st5"], P[f"{p}.post_norm.weight"], M, None, 0, None, 0, dx4, C, G[f"{p}.post_norm.weight"],
          G[f"{p}.post_norm.bias"])
-    dx3 = ff_bwd(dx4, S["x3"], S["st4"], S["h2"], "ff2", sd[3], sd[4])
+    dx3 = ff_bwd(dx4, S["x3"], S["f2"], "ff2", sd[3], sd[4])
     # ---- convolution module: x3 = x2 + W7 swish(bn(d)) + b7
     bn = S["bn"]
     dbn = _empty(M, 2 * C, dev=dev)
     gemm(A=dx3, lda=C, W=P[f"{p}.conv.net.7.weight"], sb_k=2 * C, sb_n=1, C=dbn, ldc=2 * C, M=M, N=2 * C, Cin=C, epi=EPI_DBNSWISH, aux=S["d"],
          ldaux=2 * C, e0=bn.scale, e1=bn.shift)
-    gemm(wgrad=True, A=S["d"], lda=2 * C, Cin=2 * C, pro=PRO_BN_SWISH, p0=bn.scale, p1=bn.shift, D=dx3, ldd=C, N=C, W=None,
-         C=G[f"{p}.conv.net.7.weight"], sb_k=1, sb_n=2 * C, ldc=0, M=M, dbias=G[f"{p}.conv.net.7.bias"])
+    gemm(wgrad=True, A=S["dsw"], lda=2 * C, Cin=2 * C, D=dx3, ldd=C, N=C, W=None, C=G[f"{p}.conv.net.7.weight"], sb_k=1, sb_n=2 * C, ldc=0, M=M,
+         dbias=G[f"{p}.conv.net.7.bias"])
     dd = _empty(M, 2 * C, dev=dev)
     _norm_bwd(S["d"], 2 * C, dbn, 2 * C, 1, M, 2 * C, 0, S["training"], bn, 0, None, dd, 2 * C, G[f"{p}.conv.net.5.weight"],
               G[f"{p}.conv.net.5.bias"], None, sums)
@@ -188,16 +197,19 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
          G[f"{p}.conv.net.4.conv.bias"])
     dln3 = _empty(M, C, dev=dev)
     gemm(A=dg, lda=4 * C, W=P[f"{p}.conv.net.2.weight"], sb_k=C, sb_n=1, C=dln3, ldc=C, M=M, N=C, Cin=4 * C)
-    gemm(wgrad=True, A=S["x2"], lda=C, Cin=C, pro=PRO_LN, p0=S["st3"], p1=P[f"{p}.conv.net.0.weight"], p2=P[f"{p}.conv.net.0.bias"], D=dg,
-         ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.conv.net.2.bias"])
+    gemm(wgrad=True, A=S["xn3"], lda=C, Cin=C, D=dg, ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, ldc=0, M=M,
+         dbias=G[f"{p}.conv.net.2.bias"])
     dx2 = _empty(M, C, dev=dev)
     call("cmgan_ln_bwd", dln3, C, S["x2"], C, S["st3"], P[f"{p}.conv.net.0.weight"], M, dx3, C, None, 0, dx2, C, G[f"{p}.conv.net.0.weight"],
          G[f"{p}.conv.net.0.bias"])
     # ---- attention: x2 = x1 + drop(ctx Wo^T + bo)
     dctx = _empty(M, C, dev=dev)
-    gemm(A=dx2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C, pro=PRO_DROP, pro_alpha=1.0,
-         pro_seed=sd[2], pro_drop_p=da)
-    gemm(wgrad=True, A=S["ctx"], lda=C, Cin=C, D=dx2, ldd=C, N=C, prod=1, alpha=1.0, seed=sd[2], drop_p=da, W=None,
+    if da > 0.0:
+        gemm(A=dx2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C, pro=PRO_DROP, pro_alpha=1.0,
+             pro_seed=sd[2], pro_drop_p=da)
+    else:
+        gemm(A=dx2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C)
+    gemm(wgrad=True, A=S["ctx"], lda=C, Cin=C, D=dx2, ldd=C, N=C, prod=1 if da > 0.0 else 0, alpha=1.0, seed=sd[2], drop_p=da, W=None,
          C=G[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.attn.fn.to_out.bias"])
     dqkv = _empty(M, 3 * C, dev=dev)
     delta = _empty(M, 4, dev=dev)
@@ -206,14 +218,11 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     dln2 = _empty(M, C, dev=dev)
     gemm(A=dqkv, lda=3 * C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=C)
     gemm(A=(dqkv, C), lda=3 * C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=2 * C, epi=EPI_ACC, alpha=1.0)
-    lnw, lnb = P[f"{p}.attn.norm.weight"], P[f"{p}.attn.norm.bias"]
-    gemm(wgrad=True, A=S["x1"], lda=C, Cin=C, pro=PRO_LN, p0=S["st2"], p1=lnw, p2=lnb, D=dqkv, ldd=3 * C, N=C, W=None,
-         C=G[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
-    gemm(wgrad=True, A=S["x1"], lda=C, Cin=C, pro=PRO_LN, p0=S["st2"], p1=lnw, p2=lnb, D=(dqkv, C), ldd=3 * C, N=2 * C, W=None,
-         C=G[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
+    gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=dqkv, ldd=3 * C, N=C, W=None, C=G[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
+    gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=(dqkv, C), ldd=3 * C, N=2 * C, W=None, C=G[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, ldc=0,
+         M=M)
     dx1 = _empty(M, C, dev=dev)
-    call("cmgan_ln_bwd", dln2, C, S["x1"], C, S["st2"], lnw, M, dx2, C, None, 0, dx1, C, G[f"{p}.attn.norm.weight"], G[f"{p}.attn.norm.bias"])
+    call("cmgan_ln_bwd", dln2, C, S["x1"], C, S["st2"], P[f"{p}.attn.norm.weight"], M, dx2, C, None, 0, dx1, C, G[f"{p}.attn.norm.weight"],
+         G[f"{p}.attn.norm.bias"])
     # ---- first feed-forward; the outer residual adds dy
-    return ff_bwd(dx1, S["x"], S["st1"], S["h1"], "ff1", sd[0], sd[1], res2=dy)
-
-
+    return ff_bwd(dx1, S["x"], S["f1"], "ff1", sd[0], sd[1], res2=dy)

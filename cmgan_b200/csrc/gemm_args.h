@@ -32,7 +32,9 @@ enum CmganEpi {
     CMGAN_EPI_DROP_RES = 1,    // C = alpha * drop(m * N + n) * v + R[m, n]   (R may be null)
     CMGAN_EPI_DSWISH_DROP = 2, // C = v * dswish(aux[m, n]) * drop(m * N + n)
     CMGAN_EPI_DBNSWISH = 3,    // z = aux[m, n] * e0[n] + e1[n];  C = v * dswish(z)
-    CMGAN_EPI_ACC = 4          // C = alpha * v + C
+    CMGAN_EPI_ACC = 4,         // C = alpha * v + C
+    CMGAN_EPI_SWISH_DUAL = 5   // C = v (skipped when C is null);  C2[m, n] = swish(v) * drop(m * N + n)   (feed-forward: pre-activation kept for
+                               // the backward pass, activated copy consumed by the next GEMM without a prologue)
 };
 
 typedef struct CmganGemmArgs {
@@ -52,4 +54,5 @@ typedef struct CmganGemmArgs {
     const float* D; long long ldd; int prod; float* dbias;
     int precision;             // 0 = fp32 FFMA, 1 = tf32 tcgen05 tensor cores (shapes the tensor path does not cover fall back to fp32 FFMA)
     float* ws; long long ws_floats;   // tf32 path: scratch for the re-tiled weight operand, >= N_pad * Cin * ntaps floats (caller-owned)
+    float* C2; long long ldc2;        // second output of CMGAN_EPI_SWISH_DUAL
 } CmganGemmArgs;

@@ -75,8 +75,13 @@ __global__ void __launch_bounds__(NT, 2) gemm_rows_kernel(const __grid_constant_
             int n = n0 + tx * 4 + j;
             if (n >= g.N) continue;
             float v = acc[i][j] + (g.bias ? __ldg(g.bias + n) : 0.f);
-            float* cp = g.C + m * g.ldc + n;
-            *cp = epilogue(g, v, m, n, cp);
+            if (g.epi == CMGAN_EPI_SWISH_DUAL) {
+                g.C2[m * g.ldc2 + n] = swishf_(v) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+                if (g.C) g.C[m * g.ldc + n] = v;
+            } else {
+                float* cp = g.C + m * g.ldc + n;
+                *cp = epilogue(g, v, m, n, cp);
+            }
         }
     }
 }
@@ -169,7 +174,8 @@ int validate(const CmganGemmArgs* a, const char* who) {
     CMGAN_REQUIRE(a != nullptr, "%s: null args", who);
     CMGAN_REQUIRE(a->M >= 0 && a->N > 0 && a->Cin > 0, "%s: bad shape M=%d N=%d Cin=%d", who, a->M, a->N, a->Cin);
     CMGAN_REQUIRE(a->ntaps >= 1 && a->ntaps <= CMGAN_MAX_TAPS, "%s: ntaps=%d out of range", who, a->ntaps);
-    CMGAN_REQUIRE(a->A && a->C, "%s: null A/C pointer", who);
+    CMGAN_REQUIRE(a->A && (a->C || (a->epi == CMGAN_EPI_SWISH_DUAL && a->C2)), "%s: null A/C pointer", who);
+    if (a->epi == CMGAN_EPI_SWISH_DUAL) CMGAN_REQUIRE(a->C2 != nullptr, "%s: SWISH_DUAL epilogue needs C2", who);
     if (a->conv) {
         CMGAN_REQUIRE(a->OH > 0 && a->OW > 0 && a->IH > 0 && a->IW > 0, "%s: bad conv geometry", who);
         CMGAN_REQUIRE(a->mul_y >= 1 && a->mul_x >= 1 && a->div_y >= 1 && a->div_x >= 1, "%s: bad stride", who);

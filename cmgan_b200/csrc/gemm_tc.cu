@@ -1,22 +1,24 @@
-// tf32 tensor-core implementation of the row-parallel GEMM contract (gemm_args.h) for sm_100a:
-// tcgen05.mma (kind::tf32, M = 128, N = 16..256) with the accumulator in TMEM, warp-specialised:
+// tf32 tensor-core implementation of the row-parallel GEMM contract (gemm_args.h) for sm_100a.
+// Persistent, warp-specialised: one CTA per SM loops over 128-row output tiles; the accumulator lives in TMEM and is
+// double-buffered so that the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 //
-//   warps 0-3  A producers, then epilogue.
-//              * no prologue (convolutions over materialised activations, data gradients): cp.async (LDGSTS, 16 B, zero-fill for
-//                padding rows) straight into the canonical K-major SWIZZLE_128B layout, software-pipelined two chunks deep;
+//   warps 0-3  A producers.
+//              * no prologue (convolutions / projections over materialised activations, data gradients): cp.async (LDGSTS, 16 B,
+//                zero-fill for padding rows) straight into the canonical K-major SWIZZLE_128B layout, pipelined two chunks deep;
 //                a chunk is published with cp.async.wait_group -> fence.proxy.async -> mbarrier.arrive.
-//              * with prologue (LayerNorm / BatchNorm+Swish / Swish+dropout / dropout): LDG.128 -> registers -> transform
-//                (per-chunk parameters hoisted into float4 registers) -> round to tf32 -> st.shared -> fence -> arrive.
-//              After the main loop the same warps drain the accumulator: tcgen05.ld 32x32b -> shared-memory staging ->
-//              coalesced float4 epilogue (bias, dropout, residual, activation gradients) -> global.
-//   warp 4     TMEM allocation; one lane issues tcgen05.mma and tcgen05.commit (stage release / accumulator ready).
-//   warp 5     one lane issues the weight-tile loads: cp.async.bulk (TMA bulk copy, UBLKCP) of a pre-tiled,
-//              pre-swizzled (N x 128 B) block per K chunk, completing on the stage's mbarrier.
+//              * with prologue (BatchNorm+Swish / Swish+dropout / dropout / LayerNorm): LDG.128 -> registers -> transform ->
+//                round to tf32 -> st.shared -> fence.proxy.async -> mbarrier.arrive.
+//   warp 4     TMEM allocation (2 x N columns); one lane issues tcgen05.mma (kind::tf32, M = 128, N = 16..256, K = 8) and
+//              tcgen05.commit (A-stage release, accumulator ready).
+//   warp 5     weight tiles by cp.async.bulk (TMA bulk copy, UBLKCP) of pre-tiled, pre-swizzled (N x 128 B) blocks: all K chunks
+//              once per CTA when the whole weight fits in shared memory ("resident", every conformer GEMM), else per K chunk
+//              through the same stage ring as A ("streamed", the dilated dense convolutions).
+//   warps 6-9  epilogue: tcgen05.ld 32x32b -> per-warp shared-memory staging -> coalesced float4 rows: bias, dropout, residual,
+//              activation gradients, Swish dual output -> global; then release the accumulator buffer.
 //
 // The weight operand is re-tiled once per call by pack_b_kernel into the scratch the caller passes (any source layout:
 // Linear (N,K), Conv2d (N,C,kh,kw), and the transposed forms used for data gradients).
-// One CTA computes a 128 x N output tile; two CTAs are co-resident per SM so one tile's epilogue overlaps the
-// other's main loop.  All waits are bounded (a protocol bug traps instead of hanging the GPU).
+// All waits are bounded (a protocol bug traps instead of hanging the GPU).
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_device.cuh"
@@ -26,13 +28,16 @@ namespace {
 using namespace cmgan_gemm;
 using namespace cmgan_tc;
 
-constexpr int BM = 128;              // rows per CTA tile = UMMA M
+constexpr int BM = 128;              // rows per tile = UMMA M
 constexpr int KC = 32;               // floats per K chunk = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * KC * 4;   // 16 KB
-constexpr int NPROD = 128;           // producer / epilogue threads (warps 0-3)
-constexpr int NTHREADS = 192;
+constexpr int NPROD = 128;           // producer threads (warps 0-3)
+constexpr int NTHREADS = 320;
 constexpr int SLAB = 64;             // epilogue column slab
 constexpr int STG_LD = SLAB + 4;     // staging row stride (floats): conflict-free 128-bit accesses
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;      // 34816
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int RESIDENT_MAX = 96 * 1024;
 
 // ---- weight re-tiling ------------------------------------------------------------------------------
 // out[chunk][n][swizzled 32 floats], chunk = tap * (Cin/32) + kc;  rows n >= N are zero
@@ -50,60 +55,74 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
     out[(chunk * BN + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
 }
 
-// ---- main kernel --------------------------------------------------------------------------------------
+struct TcCfg { int BN, stages, tmem_cols, resident, ntiles; };
+
 template <bool ASYNC_A>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
-                                                                    int BN, int stages, int tmem_cols) {
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
+                                                                    const TcCfg cfg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const int b_stage_bytes = BN * KC * 4;
-    const uint32_t sA = base;
-    const uint32_t sB = base + stages * A_STAGE_BYTES;
-    const uint32_t bars = sB + stages * b_stage_bytes;                  // full[stages], empty[stages], tmem_full, tmem_ptr
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (stages + s); };
-    const uint32_t tmem_full_bar = bars + 8u * (2 * stages);
-    const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * BM;
+    const int BN = cfg.BN, stages = cfg.stages;
+    const int b_tile_bytes = BN * KC * 4;
     const int cpt = g.Cin / KC;
     const int nchunks = cpt * g.ntaps;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + stages * A_STAGE_BYTES;
+    const uint32_t b_region = (uint32_t)(cfg.resident ? nchunks : stages) * b_tile_bytes;
+    const uint32_t sStg = sB + b_region;
+    const uint32_t bars = sStg + STG_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (stages + s); };
+    const uint32_t tfull_bar = bars + 8u * (2 * stages);          // [2]
+    const uint32_t tempty_bar = tfull_bar + 16u;                  // [2]
+    const uint32_t bready_bar = tempty_bar + 16u;
+    const uint32_t tmem_ptr_addr = bready_bar + 8u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = cfg.ntiles;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), NPROD + 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), NPROD + (cfg.resident ? 0 : 1)); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8u * b, 1); mbar_init(tempty_bar + 8u * b, 4); }
+        mbar_init(bready_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr_addr, (uint32_t)tmem_cols);
+    if (warp == 4) tmem_alloc(tmem_ptr_addr, (uint32_t)cfg.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    const uint32_t acc_stride = (uint32_t)(cfg.tmem_cols / 2);
 
     if (warp < 4) {
         // ================================ A producers ================================
         const int c = tid & 7;            // 16-byte chunk within the 128-byte row
         const int rr = tid >> 3;          // rows rr, rr+16, ..., rr+112
-        RowInfo ri[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ri[i] = decode_row(g, m0 + rr + 16 * i);
         uint32_t dst_off[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const int r = rr + 16 * i; dst_off[i] = r * 128 + ((c ^ (r & 7)) << 4); }
+        const long total = (long)my_tiles * nchunks;
 
         if (ASYNC_A) {
-            // ---- cp.async pipeline: issue chunk ch, publish chunk ch - LAG
             const int LAG = stages >= 3 ? 2 : 1;
-            long rowoff[8];                // element offset of the gathered row for the current tap, -1 = padding
-            int cur_tap = -1;
-            for (int ch = 0; ch < nchunks + LAG; ++ch) {
-                if (ch < nchunks) {
-                    const int s = ch % stages;
-                    const uint32_t par = (uint32_t)((ch / stages) & 1);
+            long rowoff[8];
+            RowInfo ri[8];
+            int cur_tile = -1, cur_tap = -1;
+            for (long q = 0; q < total + LAG; ++q) {
+                if (q < total) {
+                    const int lt = (int)(q / nchunks), ch = (int)(q - (long)lt * nchunks);
+                    const int s = (int)(q % stages);
+                    const uint32_t par = (uint32_t)((q / stages) & 1);
                     const int tap = ch / cpt, k0 = (ch - tap * cpt) * KC + c * 4;
+                    if (lt != cur_tile) {
+                        cur_tile = lt; cur_tap = -1;
+                        const int m0 = (blockIdx.x + lt * gridDim.x) * BM;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ri[i] = decode_row(g, m0 + rr + 16 * i);
+                    }
                     if (tap != cur_tap) {
                         cur_tap = tap;
 #pragma unroll
@@ -121,29 +140,35 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_rows_tc_kernel(const __grid_
                     }
                 }
                 cp_async_commit();
-                const int done = ch - LAG;
+                const long done = q - LAG;
                 if (done >= 0) {
                     if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
                     fence_proxy_async();
-                    mbar_arrive(full_bar(done % stages));
+                    mbar_arrive(full_bar((int)(done % stages)));
                 }
             }
         } else {
-            // ---- register path with prologue
             float mean[8], rstd[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { mean[i] = 0.f; rstd[i] = 1.f; }
-            if (g.pro == CMGAN_PRO_LN) {        // ntaps == 1: in_row is constant over the K loop
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    long r = in_row_of(g, ri[i], 0);
-                    if (r >= 0) { float2 st = __ldg(reinterpret_cast<const float2*>(g.p0) + r); mean[i] = st.x; rstd[i] = st.y; }
-                }
-            }
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int s = ch % stages;
-                const uint32_t par = (uint32_t)((ch / stages) & 1);
+            RowInfo ri[8];
+            int cur_tile = -1;
+            for (long q = 0; q < total; ++q) {
+                const int lt = (int)(q / nchunks), ch = (int)(q - (long)lt * nchunks);
+                const int s = (int)(q % stages);
+                const uint32_t par = (uint32_t)((q / stages) & 1);
                 const int tap = ch / cpt, k0 = (ch - tap * cpt) * KC + c * 4;
+                if (lt != cur_tile) {
+                    cur_tile = lt;
+                    const int m0 = (blockIdx.x + lt * gridDim.x) * BM;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        ri[i] = decode_row(g, m0 + rr + 16 * i);
+                        mean[i] = 0.f; rstd[i] = 1.f;
+                        if (g.pro == CMGAN_PRO_LN) {        // ntaps == 1: in_row is constant over the K loop
+                            long r = in_row_of(g, ri[i], 0);
+                            if (r >= 0) { float2 st = __ldg(reinterpret_cast<const float2*>(g.p0) + r); mean[i] = st.x; rstd[i] = st.y; }
+                        }
+                    }
+                }
                 ChunkParams cp;
                 load_chunk_params(g, k0, cp);
                 float4 v[8];
@@ -166,81 +191,115 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_rows_tc_kernel(const __grid_
                 mbar_arrive(full_bar(s));
             }
         }
-        // ================================ epilogue ================================
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        // all MMAs have completed -> the pipeline stages are free: reuse them as per-warp staging (32 rows x 68 floats)
-        float* stg = reinterpret_cast<float*>(base_ptr) + warp * 32 * STG_LD;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int col4 = (lane & 15) * 4;          // this lane's 4 columns within the slab
-        const int rsub = lane >> 4;                // 0/1: two rows per pass
-        for (int n0 = 0; n0 < BN; n0 += SLAB) {
-            const int ncols = min(SLAB, BN - n0);
-            for (int q = 0; q < ncols; q += 16) {
-                float acc[16];
-                tmem_ld16(trow + (uint32_t)(n0 + q), acc);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * STG_LD + q + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            }
-            __syncwarp();
-            const int n = n0 + col4;
-            if (col4 < ncols) {
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-                for (int rp = 0; rp < 32; rp += 2) {
-                    const int rl = rp + rsub;
-                    const long m = (long)m0 + warp * 32 + rl;
-                    if (m >= g.M) continue;
-                    float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
-                    float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
-                    float* cp = g.C + m * g.ldc + n;
-                    if (g.epi != CMGAN_EPI_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) vv[j] = epilogue(g, vv[j], m, n + j, cp + j);
-                    }
-                    *reinterpret_cast<float4*>(cp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                }
-            }
-            __syncwarp();
-        }
-        tc_fence_before();
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int s = ch % stages;
-                const uint32_t par = (uint32_t)((ch / stages) & 1);
-                mbar_wait(full_bar(s), par);
+            if (cfg.resident) mbar_wait(bready_bar, 0);
+            long q = 0;
+            for (int lt = 0; lt < my_tiles; ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(tempty_bar + 8u * buf, (uint32_t)(((lt >> 1) & 1) ^ 1));      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE_BYTES, 16, 1024);
-                const uint64_t bdesc = make_desc_sw128(sB + s * b_stage_bytes, 16, 1024);
+                const uint32_t tacc = tmem_base + buf * acc_stride;
+                for (int ch = 0; ch < nchunks; ++ch, ++q) {
+                    const int s = (int)(q % stages);
+                    const uint32_t par = (uint32_t)((q / stages) & 1);
+                    mbar_wait(full_bar(s), par);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE_BYTES, 16, 1024);
+                    const uint64_t bdesc = make_desc_sw128(sB + (cfg.resident ? ch : s) * b_tile_bytes, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k)       // tf32: K = 8 per instruction = 32 bytes along the swizzled row
-                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ch | k) != 0 ? 1u : 0u);
-                umma_commit(empty_bar(s));             // frees the stage once the MMAs above have read it
+                    for (int k = 0; k < KC / 8; ++k)       // tf32: K = 8 per instruction = 32 bytes along the swizzled row
+                        umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ch | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar(s));             // frees the stage once the MMAs above have read it
+                }
+                umma_commit(tfull_bar + 8u * buf);         // accumulator complete
             }
-            umma_commit(tmem_full_bar);                // accumulator complete
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ================================ weight-tile loader (TMA bulk copies) ================================
+        if (lane == 0) {
+            if (cfg.resident) {
+                mbar_arrive_expect_tx(bready_bar, (uint32_t)(nchunks * b_tile_bytes));
+                for (int ch = 0; ch < nchunks; ++ch)
+                    bulk_g2s(sB + ch * b_tile_bytes, Bp + (long)ch * BN * KC, (uint32_t)b_tile_bytes, bready_bar);
+            } else {
+                const long total = (long)my_tiles * nchunks;
+                for (long q = 0; q < total; ++q) {
+                    const int ch = (int)(q % nchunks);
+                    const int s = (int)(q % stages);
+                    const uint32_t par = (uint32_t)((q / stages) & 1);
+                    mbar_wait(empty_bar(s), par ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)b_tile_bytes);
+                    bulk_g2s(sB + s * b_tile_bytes, Bp + (long)ch * BN * KC, (uint32_t)b_tile_bytes, full_bar(s));
+                }
+            }
         }
         __syncwarp();
     } else {
-        // ================================ weight-tile loader (TMA bulk copies) ================================
-        if (lane == 0) {
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int s = ch % stages;
-                const uint32_t par = (uint32_t)((ch / stages) & 1);
-                mbar_wait(empty_bar(s), par ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), (uint32_t)b_stage_bytes);
-                bulk_g2s(sB + s * b_stage_bytes, Bp + (long)ch * BN * KC, (uint32_t)b_stage_bytes, full_bar(s));
+        // ================================ epilogue (warps 6-9) ================================
+        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
+        float* stg = reinterpret_cast<float*>(base_ptr + (sStg - base)) + (warp - 6) * 32 * STG_LD;
+        const int col4 = (lane & 15) * 4;          // this lane's 4 columns within the slab
+        const int rsub = lane >> 4;                // 0/1: two rows per pass
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int buf = lt & 1;
+            const int m0 = (blockIdx.x + lt * gridDim.x) * BM;
+            mbar_wait(tfull_bar + 8u * buf, (uint32_t)((lt >> 1) & 1));
+            tc_fence_after();
+            const uint32_t trow = tmem_base + buf * acc_stride + ((uint32_t)(q4 * 32) << 16);
+            for (int n0 = 0; n0 < BN; n0 += SLAB) {
+                const int ncols = min(SLAB, BN - n0);
+                for (int q = 0; q < ncols; q += 16) {
+                    float acc[16];
+                    tmem_ld16(trow + (uint32_t)(n0 + q), acc);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * STG_LD + q + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                }
+                if (n0 + SLAB >= BN) {                        // last slab read: the accumulator buffer may be overwritten
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + 8u * buf);
+                }
+                __syncwarp();
+                const int n = n0 + col4;
+                if (col4 < ncols) {
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                    for (int rp = 0; rp < 32; rp += 2) {
+                        const int rl = rp + rsub;
+                        const long m = (long)m0 + q4 * 32 + rl;
+                        if (m >= g.M) continue;
+                        float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
+                        float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
+                        if (g.epi == CMGAN_EPI_SWISH_DUAL) {
+                            if (g.C) *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            float o[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                o[j] = swishf_(vv[j]) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n + j, g.drop_thr, g.inv_keep);
+                            *reinterpret_cast<float4*>(g.C2 + m * g.ldc2 + n) = make_float4(o[0], o[1], o[2], o[3]);
+                            continue;
+                        }
+                        float* cp = g.C + m * g.ldc + n;
+                        if (g.epi != CMGAN_EPI_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) vv[j] = epilogue(g, vv[j], m, n + j, cp + j);
+                        }
+                        *reinterpret_cast<float4*>(cp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    }
+                }
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+        tmem_dealloc(tmem_base, (uint32_t)cfg.tmem_cols);
     }
 }
 
@@ -248,7 +307,8 @@ int tc_supported(const CmganGemmArgs* a) {
     if (a->N % 16 || a->N < 16 || a->N > 256) return 0;
     if (a->Cin % KC) return 0;
     if (a->lda % 4 || ((uintptr_t)a->A & 15)) return 0;
-    if (a->ldc % 4 || ((uintptr_t)a->C & 15)) return 0;
+    if (a->C && (a->ldc % 4 || ((uintptr_t)a->C & 15))) return 0;
+    if (a->epi == CMGAN_EPI_SWISH_DUAL && (a->ldc2 % 4 || ((uintptr_t)a->C2 & 15))) return 0;
     if (a->bias && ((uintptr_t)a->bias & 15)) return 0;
     for (int t = 0; t < a->ntaps; ++t)
         if (a->tap_off[t] % 4) return 0;
@@ -260,34 +320,40 @@ int tc_supported(const CmganGemmArgs* a) {
     return 1;
 }
 
+int g_num_sms = 0;
+
 }  // namespace
 
 // tf32 tensor-core path of cmgan_gemm_rows (same contract).  Returns 1 if the shape is not covered (caller falls back).
 int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     if (!tc_supported(a)) return 1;
-    const int BN = a->N;
-    const int b_stage = BN * KC * 4;
-    int stages = (100 * 1024 - 2048) / (A_STAGE_BYTES + b_stage);
-    if (stages > 4) stages = 4;
-    if (stages < 2) stages = 2;
+    TcCfg cfg;
+    cfg.BN = a->N;
+    const int b_tile = cfg.BN * KC * 4;
     const int nchunks = (a->Cin / KC) * a->ntaps;
-    // the epilogue staging (4 warps x 32 rows x 68 floats = 34816 B) lives in the stage memory
-    while ((size_t)stages * (A_STAGE_BYTES + b_stage) < 4 * 32 * STG_LD * sizeof(float)) ++stages;
-    int tmem_cols = 32;
-    while (tmem_cols < BN) tmem_cols <<= 1;
-    const size_t smem = (size_t)stages * (A_STAGE_BYTES + b_stage) + 1024 /*alignment*/ + 8 * (2 * stages + 2) + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
-        if (e != cudaSuccess) { cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-        attr_set = true;
+    cfg.resident = (long)nchunks * b_tile <= RESIDENT_MAX ? 1 : 0;
+    const int fixed = 1024 /*alignment*/ + STG_BYTES + 256 /*barriers*/ + (cfg.resident ? nchunks * b_tile : 0);
+    const int per_stage = A_STAGE_BYTES + (cfg.resident ? 0 : b_tile);
+    cfg.stages = (SMEM_LIMIT - fixed) / per_stage;
+    if (cfg.stages > 6) cfg.stages = 6;
+    if (cfg.stages < 2) return 1;
+    cfg.tmem_cols = 64;
+    while (cfg.tmem_cols < 2 * cfg.BN) cfg.tmem_cols <<= 1;
+    cfg.ntiles = cdiv(a->M, BM);
+    const size_t smem = (size_t)fixed + (size_t)cfg.stages * per_stage;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) { g_num_sms = 0; cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     }
-    (void)nchunks;
-    long total = (long)nchunks * BN * KC;
-    pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, BN, a->ws);
+    long total = (long)nchunks * cfg.BN * KC;
+    pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
     if (cmgan_check_launch("pack_b_kernel")) return -1;
-    if (a->pro == CMGAN_PRO_NONE) gemm_rows_tc_kernel<true><<<cdiv(a->M, BM), NTHREADS, smem, st>>>(*a, a->ws, BN, stages, tmem_cols);
-    else gemm_rows_tc_kernel<false><<<cdiv(a->M, BM), NTHREADS, smem, st>>>(*a, a->ws, BN, stages, tmem_cols);
+    const int grid = cfg.ntiles < g_num_sms ? cfg.ntiles : g_num_sms;
+    if (a->pro == CMGAN_PRO_NONE) gemm_rows_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(*a, a->ws, cfg);
+    else gemm_rows_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(*a, a->ws, cfg);
     return cmgan_check_launch("gemm_rows_tc_kernel");
 }

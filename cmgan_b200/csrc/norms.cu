@@ -26,7 +26,7 @@ __global__ void ln_stats_kernel(const float* __restrict__ x, long ldx, long M, f
 // y = LN(x) * gamma + beta (+ res);  stats written for the backward pass
 __global__ void ln_apply_kernel(const float* __restrict__ x, long ldx, long M, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ res, long ldr,
-                                float* __restrict__ y, long ldy, float2* __restrict__ stats) {
+                                float* __restrict__ y, long ldy, float2* __restrict__ stats, int round_tf32) {
     long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -39,6 +39,12 @@ __global__ void ln_apply_kernel(const float* __restrict__ x, long ldx, long M, c
     float2 b = __ldg(reinterpret_cast<const float2*>(beta) + lane);
     float2 o = make_float2(d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y);
     if (res) { float2 r = __ldg(reinterpret_cast<const float2*>(res + row * ldr) + lane); o.x += r.x; o.y += r.y; }
+    if (round_tf32) {      // consumer is a tf32 tensor-core GEMM fed by cp.async: round (not truncate) once, here
+        uint32_t a, b;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(o.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(o.y));
+        o = make_float2(__uint_as_float(a), __uint_as_float(b));
+    }
     reinterpret_cast<float2*>(y + row * ldy)[lane] = o;
     if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
 }
@@ -264,11 +270,11 @@ CMGAN_API int cmgan_ln_stats(const float* x, long long ldx, long long M, float* 
 
 // y = LayerNorm(x) * gamma + beta + res  (res, stats optional); reference conformer.py:214,222 + generator.py:95,97
 CMGAN_API int cmgan_ln_apply(const float* x, long long ldx, long long M, const float* gamma, const float* beta,
-                             const float* res, long long ldr, float* y, long long ldy, float* stats, void* stream) {
+                             const float* res, long long ldr, float* y, long long ldy, float* stats, int round_tf32, void* stream) {
     CMGAN_REQUIRE(x && y && gamma && beta && ldx % 2 == 0 && ldy % 2 == 0 && ldr % 2 == 0, "cmgan_ln_apply: bad arguments");
     if (M == 0) return 0;
     ln_apply_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, M, gamma, beta, res, ldr, y, ldy,
-                                                                 reinterpret_cast<float2*>(stats));
+                                                                 reinterpret_cast<float2*>(stats), round_tf32);
     return cmgan_check_launch("ln_apply_kernel");
 }
 

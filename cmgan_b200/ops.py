@@ -20,7 +20,7 @@ PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" els
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
 PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
-EPI_NONE, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_DBNSWISH, EPI_ACC = range(5)
+EPI_NONE, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_DBNSWISH, EPI_ACC, EPI_SWISH_DUAL = range(6)
 
 Ptr = Union[None, torch.Tensor, Tuple[torch.Tensor, int]]
 
@@ -68,7 +68,8 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
          pro: int = PRO_NONE, pro_alpha: float = 1.0, p0: Ptr = None, p1: Ptr = None, p2: Ptr = None, rows_per_batch: int = 0, pstride: int = 0,
          epi: int = EPI_NONE, alpha: float = 1.0, R: Ptr = None, ldr: int = 0, aux: Ptr = None, ldaux: int = 0, e0: Ptr = None, e1: Ptr = None,
          seed: int = 0, drop_p: float = 0.0, pro_seed: int = 0, pro_drop_p: float = 0.0,
-         wgrad: bool = False, D: Ptr = None, ldd: int = 0, prod: int = 0, dbias: Ptr = None, precision: Optional[int] = None) -> None:
+         wgrad: bool = False, D: Ptr = None, ldd: int = 0, prod: int = 0, dbias: Ptr = None, precision: Optional[int] = None,
+         C2: Ptr = None, ldc2: int = 0) -> None:
     """One dense contraction (see csrc/gemm_args.h).  ``conv`` = dict(OH, OW, IH, IW, mul_y, mul_x, div_y, div_x);
     ``taps`` = [(dy, dx), ...].  With ``wgrad`` the call accumulates dW (laid out like W) into ``C``."""
     a = GemmArgs()
@@ -101,6 +102,7 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
     a.pro_seed = pro_seed & 0xFFFFFFFFFFFFFFFF
     a.pro_thr, a.pro_inv_keep = drop_params(pro_drop_p)
     a.D, a.ldd, a.prod, a.dbias = ptr(D), ldd, prod, ptr(dbias)
+    a.C2, a.ldc2 = ptr(C2), ldc2
     a.precision = PRECISION if precision is None else precision
     ws = None
     if a.precision == 1 and not wgrad and N % 16 == 0 and N <= 256 and Cin % 32 == 0:

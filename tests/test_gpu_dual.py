@@ -1,0 +1,41 @@
+"""Swish dual-output GEMM epilogue (feed-forward hidden layer): fp32 FFMA path vs float64, tf32 tcgen05 path vs fp32."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+if torch.cuda.is_available():
+    from cmgan_b200 import ops
+    from cmgan_b200.ops import call, gemm
+
+
+def test_swish_dual_epilogue():
+    M, K, N = 1500, 64, 256
+    g = torch.Generator().manual_seed(3)
+    x, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.2, torch.randn(N, generator=g)
+    seed, p = 99, 0.2
+    thr, inv = ops.drop_params(p)
+    mask = torch.empty(M * N, device=DEV)
+    call("cmgan_dropout_mask", mask, M * N, seed, thr)
+    keep = mask.view(M, N).double().cpu()
+    h_ref = x.double() @ W.double().t() + b.double()
+    a_ref = h_ref * torch.sigmoid(h_ref) * keep * inv
+    outs = {}
+    for prec in (0, 1):
+        h = torch.zeros(M, N, device=DEV)
+        a = torch.zeros(M, N, device=DEV)
+        gemm(A=x.to(DEV), lda=K, W=W.to(DEV), sb_k=1, sb_n=K, bias=b.to(DEV), C=h, ldc=N, M=M, N=N, Cin=K, epi=ops.EPI_SWISH_DUAL, C2=a, ldc2=N,
+             seed=seed, drop_p=p, precision=prec)
+        a_only = torch.zeros(M, N, device=DEV)
+        gemm(A=x.to(DEV), lda=K, W=W.to(DEV), sb_k=1, sb_n=K, bias=b.to(DEV), C=None, ldc=N, M=M, N=N, Cin=K, epi=ops.EPI_SWISH_DUAL, C2=a_only,
+             ldc2=N, seed=seed, drop_p=p, precision=prec)
+        torch.cuda.synchronize()
+        assert torch.equal(a, a_only)
+        outs[prec] = (h.double().cpu(), a.double().cpu())
+    tol = {0: 3e-6, 1: 4e-3}
+    for prec in (0, 1):
+        for name, got, ref in (("h", outs[prec][0], h_ref), ("a", outs[prec][1], a_ref)):
+            err = (got - ref).abs().max().item()
+            print(f"[parity] swish-dual prec={prec} {name}: max-abs {err:.3e} (range {ref.abs().max().item():.3e})")
+            assert err <= tol[prec] * ref.abs().max().item()

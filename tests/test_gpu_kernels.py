@@ -162,7 +162,7 @@ def test_layernorm_fwd_bwd():
     xd = x.detach().float().to(DEV)
     yd = torch.empty(M, 64, device=DEV)
     st = torch.empty(M, 2, device=DEV)
-    call("cmgan_ln_apply", xd, 64, M, g.detach().float().to(DEV), b.detach().float().to(DEV), res.to(DEV), 64, yd, 64, st)
+    call("cmgan_ln_apply", xd, 64, M, g.detach().float().to(DEV), b.detach().float().to(DEV), res.to(DEV), 64, yd, 64, st, 0)
     _chk(yd, y, 3e-6, "ln_apply")
     dx = torch.empty(M, 64, device=DEV)
     dg, db = torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
