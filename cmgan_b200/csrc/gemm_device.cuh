@@ -139,4 +139,46 @@ __device__ __forceinline__ float4 transform4(const CmganGemmArgs& g, float4 v, l
     return v;
 }
 
+// ---- vectorised epilogue on 4 consecutive columns; `ex` = the pre-loaded auxiliary operand of the same 4 positions
+// (R for DROP_RES, aux for DSWISH_DROP / DBNSWISH, the old C for ACC), `e0v`/`e1v` = per-column scale/shift (DBNSWISH)
+__device__ __forceinline__ bool epi_needs_extra(const CmganGemmArgs& g) {
+    return (g.epi == CMGAN_EPI_DROP_RES && g.R != nullptr) || g.epi == CMGAN_EPI_DSWISH_DROP || g.epi == CMGAN_EPI_DBNSWISH || g.epi == CMGAN_EPI_ACC;
+}
+__device__ __forceinline__ const float* epi_extra_ptr(const CmganGemmArgs& g, long m, int n) {
+    switch (g.epi) {
+        case CMGAN_EPI_DROP_RES: return g.R + m * g.ldr + n;
+        case CMGAN_EPI_DSWISH_DROP:
+        case CMGAN_EPI_DBNSWISH: return g.aux + m * g.ldaux + n;
+        default: return g.C + m * g.ldc + n;
+    }
+}
+__device__ __forceinline__ void epilogue4(const CmganGemmArgs& g, float v[4], long m, int n, const float4& ex, const float4& e0v, const float4& e1v) {
+    const float x[4] = {ex.x, ex.y, ex.z, ex.w};
+    switch (g.epi) {
+        case CMGAN_EPI_DROP_RES: {
+            const uint64_t idx = (uint64_t)m * g.N + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = g.alpha * v[j] * cmgan_drop_scale(g.seed, idx + j, g.drop_thr, g.inv_keep) + (g.R ? x[j] : 0.f);
+            break;
+        }
+        case CMGAN_EPI_DSWISH_DROP: {
+            const uint64_t idx = (uint64_t)m * g.N + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(x[j]) * cmgan_drop_scale(g.seed, idx + j, g.drop_thr, g.inv_keep);
+            break;
+        }
+        case CMGAN_EPI_DBNSWISH: {
+            const float a[4] = {e0v.x, e0v.y, e0v.z, e0v.w}, b[4] = {e1v.x, e1v.y, e1v.z, e1v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(fmaf(x[j], a[j], b[j]));
+            break;
+        }
+        case CMGAN_EPI_ACC:
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = g.alpha * v[j] + x[j];
+            break;
+        default: break;
+    }
+}
+
 }  // namespace cmgan_gemm

