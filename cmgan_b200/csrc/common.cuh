@@ -22,7 +22,7 @@ int cmgan_check_launch(const char* what);   // cudaGetLastError() -> 0 / -1 (+ m
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- math ----------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x * sigmoid(x)]
 __device__ __forceinline__ float dswishf_(float x) {
@@ -43,18 +43,28 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---- dropout --------------------------------------------------------------------------------------
 // Counter-based keep decision: a function of (seed, element index) only, so the backward pass (and the
-// test-side mask export) regenerate exactly the mask the forward pass applied.  splitmix64 finaliser.
-__host__ __device__ __forceinline__ uint32_t cmgan_hash(uint64_t seed, uint64_t idx) {
-    uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+// test-side mask export) regenerate exactly the mask the forward pass applied.  One 32-bit hash (lowbias32 mixer)
+// serves two consecutive elements (16 bits each), so the float4 epilogues pay two hashes per four elements.
+__host__ __device__ __forceinline__ uint32_t cmgan_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
 }
-// returns 0 (dropped) or 1/(1-p) (kept); thr = p * 2^32 (0 => dropout disabled => 1)
+__host__ __device__ __forceinline__ uint32_t cmgan_seed32(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u); }
+__host__ __device__ __forceinline__ uint32_t cmgan_pair_hash(uint32_t seed32, uint64_t pair) { return cmgan_mix32(((uint32_t)pair * 0x9E3779B1u) ^ seed32); }
+// returns 0 (dropped) or 1/(1-p) (kept); thr = p * 2^32 (0 => dropout disabled => 1); the decision uses the top 16 bits of thr
 __host__ __device__ __forceinline__ float cmgan_drop_scale(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep) {
     if (thr == 0u) return 1.0f;
-    return cmgan_hash(seed, idx) >= thr ? inv_keep : 0.0f;
+    const uint32_t h = cmgan_pair_hash(cmgan_seed32(seed), idx >> 1);
+    const uint32_t r = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+    return r >= (thr >> 16) ? inv_keep : 0.0f;
+}
+// four consecutive elements starting at idx (idx % 4 == 0): two hashes
+__host__ __device__ __forceinline__ void cmgan_drop_scale4(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep, float out[4]) {
+    if (thr == 0u) { out[0] = out[1] = out[2] = out[3] = 1.0f; return; }
+    const uint32_t s = cmgan_seed32(seed), t = thr >> 16;
+    const uint32_t h0 = cmgan_pair_hash(s, idx >> 1), h1 = cmgan_pair_hash(s, (idx >> 1) + 1);
+    out[0] = (h0 & 0xFFFFu) >= t ? inv_keep : 0.0f; out[1] = (h0 >> 16) >= t ? inv_keep : 0.0f;
+    out[2] = (h1 & 0xFFFFu) >= t ? inv_keep : 0.0f; out[3] = (h1 >> 16) >= t ? inv_keep : 0.0f;
 }
 
 // ---- sequence geometry -----------------------------------------------------------------------------

@@ -110,18 +110,16 @@ __device__ __forceinline__ float4 transform4(const CmganGemmArgs& g, float4 v, l
         case CMGAN_PRO_SWISH_DROP: {
             v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
             if (g.pro_thr) {
-                uint64_t idx = (uint64_t)r * g.Cin + k;
-                v.x *= cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep); v.y *= cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
-                v.z *= cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep); v.w *= cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
+                float ds[4];
+                cmgan_drop_scale4(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep, ds);
+                v.x *= ds[0]; v.y *= ds[1]; v.z *= ds[2]; v.w *= ds[3];
             }
             break;
         }
         case CMGAN_PRO_DROP: {
-            uint64_t idx = (uint64_t)r * g.Cin + k;
-            v.x *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx, g.pro_thr, g.pro_inv_keep);
-            v.y *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 1, g.pro_thr, g.pro_inv_keep);
-            v.z *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 2, g.pro_thr, g.pro_inv_keep);
-            v.w *= g.pro_alpha * cmgan_drop_scale(g.pro_seed, idx + 3, g.pro_thr, g.pro_inv_keep);
+            float ds[4];
+            cmgan_drop_scale4(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep, ds);
+            v.x *= g.pro_alpha * ds[0]; v.y *= g.pro_alpha * ds[1]; v.z *= g.pro_alpha * ds[2]; v.w *= g.pro_alpha * ds[3];
             break;
         }
         case CMGAN_PRO_IN_PRELU: {
@@ -156,15 +154,17 @@ __device__ __forceinline__ void epilogue4(const CmganGemmArgs& g, float v[4], lo
     const float x[4] = {ex.x, ex.y, ex.z, ex.w};
     switch (g.epi) {
         case CMGAN_EPI_DROP_RES: {
-            const uint64_t idx = (uint64_t)m * g.N + n;
+            float ds[4];
+            cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, ds);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = g.alpha * v[j] * cmgan_drop_scale(g.seed, idx + j, g.drop_thr, g.inv_keep) + (g.R ? x[j] : 0.f);
+            for (int j = 0; j < 4; ++j) v[j] = g.alpha * v[j] * ds[j] + (g.R ? x[j] : 0.f);
             break;
         }
         case CMGAN_EPI_DSWISH_DROP: {
-            const uint64_t idx = (uint64_t)m * g.N + n;
+            float ds[4];
+            cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, ds);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(x[j]) * cmgan_drop_scale(g.seed, idx + j, g.drop_thr, g.inv_keep);
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(x[j]) * ds[j];
             break;
         }
         case CMGAN_EPI_DBNSWISH: {

@@ -125,11 +125,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                             if (m < mend) {
                                 dv[u] = __ldg(reinterpret_cast<const float4*>(g.D + m * g.ldd + cc * 4));
                                 if (g.prod == 1) {
-                                    uint64_t idx = (uint64_t)m * g.N + cc * 4;
-                                    dv[u].x *= g.alpha * cmgan_drop_scale(g.seed, idx, g.drop_thr, g.inv_keep);
-                                    dv[u].y *= g.alpha * cmgan_drop_scale(g.seed, idx + 1, g.drop_thr, g.inv_keep);
-                                    dv[u].z *= g.alpha * cmgan_drop_scale(g.seed, idx + 2, g.drop_thr, g.inv_keep);
-                                    dv[u].w *= g.alpha * cmgan_drop_scale(g.seed, idx + 3, g.drop_thr, g.inv_keep);
+                                    float ds[4];
+                                    cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + cc * 4, g.drop_thr, g.inv_keep, ds);
+                                    dv[u].x *= g.alpha * ds[0]; dv[u].y *= g.alpha * ds[1]; dv[u].z *= g.alpha * ds[2]; dv[u].w *= g.alpha * ds[3];
                                 }
                             }
                         }
