@@ -44,7 +44,7 @@ class GemmArgs(ctypes.Structure):
 
 _CTYPE = {
     "int": ctypes.c_int, "long long": ctypes.c_longlong, "unsigned long long": ctypes.c_ulonglong,
-    "unsigned int": ctypes.c_uint, "float": ctypes.c_float,
+    "unsigned int": ctypes.c_uint, "float": ctypes.c_float, "double": ctypes.c_double,
 }
 
 

@@ -74,7 +74,7 @@ __global__ void uncompress_kernel(const float* __restrict__ re_p, const float* _
 
 // gradient of the un-compression: dU (B*T, 402) -> d_re, d_im planes (B, T, F) contiguous
 __global__ void uncompress_bwd_kernel(const float* __restrict__ re_p, const float* __restrict__ im_p, long sb, long st, long sf, long total, int T,
-                                      const float* __restrict__ dU, float* __restrict__ dre, float* __restrict__ dim_) {
+                                      const float* __restrict__ dU, float* __restrict__ dre, float* __restrict__ dim_, int accumulate) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int f = (int)(i % NF);
@@ -389,11 +389,11 @@ CMGAN_API int cmgan_uncompress(const float* re, const float* im, long long sb, l
 }
 
 CMGAN_API int cmgan_uncompress_bwd(const float* re, const float* im, long long sb, long long st, long long sf, int B, int T, const float* dU,
-                                   float* dre, float* dim_, void* stream) {
+                                   float* dre, float* dim_, int accumulate, void* stream) {
     CMGAN_REQUIRE(re && im && dU && dre && dim_, "cmgan_uncompress_bwd: null pointer");
     long total = (long)B * T * NF;
     if (total == 0) return 0;
-    uncompress_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(re, im, sb, st, sf, total, T, dU, dre, dim_);
+    uncompress_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(re, im, sb, st, sf, total, T, dU, dre, dim_, accumulate);
     return cmgan_check_launch("uncompress_bwd_kernel");
 }
 

@@ -96,8 +96,24 @@ def _sn_bwd(P, G, key, w_sn, dw_sn, sigma):
     call("cmgan_spectral_norm_bwd", w_sn, dw_sn, R, w.numel() // R, P[key + ".weight_u"], P[key + ".weight_v"], sigma, G[key + ".weight_orig"])
 
 
+class _Sink(dict):
+    """gradient target that discards everything (generator step: the discriminator's own gradients are not needed)"""
+
+    def __init__(self, P):
+        super().__init__()
+        self._scratch = {}
+        self._P = P
+
+    def __missing__(self, k):
+        t = torch.empty_like(self._P[k])
+        self[k] = t
+        return t
+
+
 def disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
     dev = dout.device
+    if G is None:
+        G = _Sink(P)
     B, H, W = S["x_shape"]
     sums = _Sums((16 + 32 + 64 + 128) * B * 2 * 2 + 64, dev)
     dout = dout.contiguous()

@@ -85,27 +85,45 @@ def stft_compress(wav: torch.Tensor, scale: torch.Tensor = None) -> torch.Tensor
     call("cmgan_pad_reflect", wav, wav.stride(0), B, L, scale, xp, Lp)
     S = torch.empty(B * T, 2 * NF, device=dev)
     gemm(A=xp, lda=HOP, W=_fwd_basis(dev), sb_k=2 * NF, sb_n=1, C=S, ldc=2 * NF, M=B * T, N=2 * NF, Cin=N_FFT, taps=[(0, 0)],
-         conv=dict(OH=1, OW=T, IH=1, IW=Lp // HOP))
+         conv=dict(OH=1, OW=T, IH=1, IW=Lp // HOP), precision=0)      # the DFTs stay exact fp32
     X = torch.empty(B, 2, T, NF, device=dev)
     call("cmgan_compress", S, B, T, X)
     return X.permute(0, 1, 3, 2)
 
 
+def uncompress_istft_fwd(fr: torch.Tensor, fi: torch.Tensor, c_div: torch.Tensor = None) -> torch.Tensor:
+    """un-compress (B,1,T,F) x 2 -> inverse DFT (GEMM) -> overlap-add -> (B, 100 (T-1)); no autograd"""
+    dev = fr.device
+    B, _, T, F = fr.shape
+    assert F == NF and fi.stride() == fr.stride()
+    s = fr.stride()
+    U = torch.empty(B * T, 2 * NF, device=dev)
+    call("cmgan_uncompress", fr, fi, s[0], s[2], s[3], B, T, U)
+    frames = torch.empty(B * T, N_FFT, device=dev)
+    gemm(A=U, lda=2 * NF, W=_inv_basis(dev), sb_k=N_FFT, sb_n=1, C=frames, ldc=N_FFT, M=B * T, N=N_FFT, Cin=2 * NF, precision=0)
+    y = torch.empty(B, HOP * (T - 1), device=dev)
+    call("cmgan_ola", frames, B, T, _inv_envelope(T, dev), c_div, y, y.stride(0))
+    return y
+
+
+def uncompress_istft_bwd(fr: torch.Tensor, fi: torch.Tensor, dy: torch.Tensor, dre: torch.Tensor, dim: torch.Tensor, accumulate: bool) -> None:
+    """gradient of uncompress_istft_fwd wrt (fr, fi) written (or added) into dre / dim ((B,1,T,F) contiguous)"""
+    dev = fr.device
+    B, _, T, F = fr.shape
+    dframes = torch.empty(B * T, N_FFT, device=dev)
+    call("cmgan_ola_bwd", dy, dy.stride(0), B, T, _inv_envelope(T, dev), dframes)
+    dU = torch.empty(B * T, 2 * NF, device=dev)
+    gemm(A=dframes, lda=N_FFT, W=_inv_basis(dev), sb_k=1, sb_n=N_FFT, C=dU, ldc=2 * NF, M=B * T, N=2 * NF, Cin=N_FFT, precision=0)
+    s = fr.stride()
+    call("cmgan_uncompress_bwd", fr, fi, s[0], s[2], s[3], B, T, dU, dre, dim, 1 if accumulate else 0)
+
+
 class _UncompressISTFT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fr, fi, c_div):
-        dev = fr.device
-        B, _, T, F = fr.shape
-        assert F == NF
         if fi.stride() != fr.stride():
             fr, fi = fr.contiguous(), fi.contiguous()
-        s = fr.stride()
-        U = torch.empty(B * T, 2 * NF, device=dev)
-        call("cmgan_uncompress", fr, fi, s[0], s[2], s[3], B, T, U)
-        frames = torch.empty(B * T, N_FFT, device=dev)
-        gemm(A=U, lda=2 * NF, W=_inv_basis(dev), sb_k=N_FFT, sb_n=1, C=frames, ldc=N_FFT, M=B * T, N=N_FFT, Cin=2 * NF)
-        y = torch.empty(B, HOP * (T - 1), device=dev)
-        call("cmgan_ola", frames, B, T, _inv_envelope(T, dev), c_div, y, y.stride(0))
+        y = uncompress_istft_fwd(fr, fi, c_div)
         ctx.save_for_backward(fr, fi)
         ctx.has_c = c_div is not None
         return y
@@ -114,17 +132,10 @@ class _UncompressISTFT(torch.autograd.Function):
     def backward(ctx, dy):
         fr, fi = ctx.saved_tensors
         assert not ctx.has_c, "the de-normalised (evaluation) path is inference only"
-        dev = fr.device
         B, _, T, F = fr.shape
-        dy = dy.contiguous()
-        dframes = torch.empty(B * T, N_FFT, device=dev)
-        call("cmgan_ola_bwd", dy, dy.stride(0), B, T, _inv_envelope(T, dev), dframes)
-        dU = torch.empty(B * T, 2 * NF, device=dev)
-        gemm(A=dframes, lda=N_FFT, W=_inv_basis(dev), sb_k=1, sb_n=N_FFT, C=dU, ldc=2 * NF, M=B * T, N=2 * NF, Cin=N_FFT)
-        s = fr.stride()
-        dre = torch.empty(B, 1, T, F, device=dev)
-        dim = torch.empty(B, 1, T, F, device=dev)
-        call("cmgan_uncompress_bwd", fr, fi, s[0], s[2], s[3], B, T, dU, dre, dim)
+        dre = torch.empty(B, 1, T, F, device=fr.device)
+        dim = torch.empty(B, 1, T, F, device=fr.device)
+        uncompress_istft_bwd(fr, fi, dy.contiguous(), dre, dim, False)
         return dre, dim, None
 
 

@@ -52,7 +52,7 @@ int cmgan_rms_scale(const float* x, long long ldx, int B, int L, float* c, void*
 int cmgan_pad_reflect(const float* x, long long ldx, int B, int L, const float* c, float* xp, int Lp, void* stream);
 int cmgan_compress(const float* S, int B, int T, float* X, void* stream);
 int cmgan_uncompress(const float* re, const float* im, long long sb, long long st, long long sf, int B, int T, float* U, void* stream);
-int cmgan_uncompress_bwd(const float* re, const float* im, long long sb, long long st, long long sf, int B, int T, const float* dU, float* dre, float* dim_, void* stream);
+int cmgan_uncompress_bwd(const float* re, const float* im, long long sb, long long st, long long sf, int B, int T, const float* dU, float* dre, float* dim_, int accumulate, void* stream);
 int cmgan_power_law(const float* re, const float* im, long long i0, long long i1, long long i2, float* ore, float* oim, long long o0, long long o1, long long o2, int d0, int d1, int d2, float p, void* stream);
 int cmgan_power_law_bwd(const float* re, const float* im, long long i0, long long i1, long long i2, const float* gre, const float* gim, long long o0, long long o1, long long o2, float* dre, float* dim_, long long q0, long long q1, long long q2, int d0, int d1, int d2, float p, void* stream);
 int cmgan_ola(const float* frames, int B, int T, const float* inv_env, const float* c_div, float* y, long long ldy, void* stream);
@@ -78,6 +78,14 @@ int cmgan_drop_prelu(const float* x, long long n, int C, const float* slope, uns
 int cmgan_drop_prelu_bwd(const float* x, const float* dy, long long n, int C, const float* slope, unsigned long long seed, unsigned int thr, float inv_keep, float* dx, float* dslope, void* stream);
 int cmgan_lsigmoid(const float* x, long long n, const float* slope, float* y, void* stream);
 int cmgan_lsigmoid_bwd(const float* x, const float* y, const float* dy, long long n, const float* slope, float* dx, float* dslope, void* stream);
+
+/* ---- losses with fused gradients (train.py:124-174) and flat AdamW (train.py:63-66) */
+int cmgan_spec_loss(const float* er, const float* ei, const float* cr, const float* ci, long long per, long long cb, long long n, float w_ri, float w_mag, double* acc, float* d_er, float* d_ei, float* est_mag, float* clean_mag, void* stream);
+int cmgan_time_loss(const float* ea, long long lde, const float* clean, long long ldc, int B, int L, float w_t, double* acc, float* d_ea, void* stream);
+int cmgan_gen_loss_finalize(const double* acc, double n_spec, double n_time, float w_ri, float w_mag, float w_t, float w_gan, const float* fake, int B, float* loss, float* d_fake, void* stream);
+int cmgan_disc_loss(const float* d_max, const float* d_enh, const float* target, int B, float* loss, float* g_max, float* g_enh, void* stream);
+int cmgan_mag_bwd_add(const float* er, const float* ei, const float* d_mag, long long gb, long long gt, long long gf, int B, int T, int F, float* d_er, float* d_ei, void* stream);
+int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd, int step, void* stream);
 
 #ifdef __cplusplus
 }
