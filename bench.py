@@ -215,12 +215,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, K):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(K):
             fn()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / K       # host time to enqueue one step (Python + launches)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -238,6 +242,7 @@ def run_ours(args):
     l0 = ops.LAUNCHES
     ms = timed(lambda: step(clean, noisy), args.steps)
     launches = ops.LAUNCHES - l0
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -298,7 +303,7 @@ def run_ours(args):
                        "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
                        "weights": "torch.manual_seed(0) default init"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * CLIP * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
             "roofline": roofline,
             "forward_only": {"value": fwd_value, "unit": UNIT, "ms_per_step": ms_f / args.steps, "workload": f"configs[1]: eval forward, batch {B} x 2 s"},

@@ -1,34 +1,40 @@
 // GLU + depthwise Conv1d(k = 31, zero pad 15/15, bias) of the conformer convolution module.
 // Reference: conformer.py:30-48,164-168.  Input g (M, 256) = pointwise-conv output, u = g[:, :128] * sigmoid(g[:, 128:]),
 // out[tok, c] = bias[c] + sum_k w[c, k] * u[tok + k - 15, c] along the sequence axis (strided rows, SeqGeom).
-// HBM-bound: one pass over g, one write of out; the 31-tap window lives in shared memory.
+// HBM-bound: one pass over g, one write of out; the 31-tap window lives in shared memory (staged with 128-bit loads, all of a
+// tile's loads in flight before the first use).
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 
 namespace {
 
 constexpr int CH = 128, KS = 31, PADL = 15, TT = 32, ROWS = TT + KS - 1;   // 62 staged rows per tile
+constexpr int C4 = CH / 4;
 
-__device__ __forceinline__ void stage_glu(float* U, const float* __restrict__ g, long base, long tok_stride, int t0, int L) {
-    // U[r][c], r in [0, ROWS): token t0 - 15 + r
-    for (int idx = threadIdx.x; idx < ROWS * CH; idx += blockDim.x) {
-        int r = idx / CH, c = idx % CH;
-        int tok = t0 - PADL + r;
-        float u = 0.f;
+// U[r][c] = a * sigmoid(b) for tokens t0 - 15 + r;  SG (optional, TT rows) = sigmoid(b) of the centre rows
+__device__ __forceinline__ void stage_glu(float* U, float* SG, const float* __restrict__ g, long base, long tok_stride, int t0, int L) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < ROWS * C4; idx += blockDim.x) {
+        const int r = idx / C4, c4 = idx % C4;
+        const int tok = t0 - PADL + r;
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f), s = u;
         if (tok >= 0 && tok < L) {
-            const float* p = g + (base + (long)tok * tok_stride) * (2 * CH);
-            u = __ldg(p + c) * sigmoidf_(__ldg(p + CH + c));
+            const float4* p = reinterpret_cast<const float4*>(g + (base + (long)tok * tok_stride) * (2 * CH));
+            const float4 a = __ldg(p + c4), b = __ldg(p + C4 + c4);
+            s = make_float4(sigmoidf_(b.x), sigmoidf_(b.y), sigmoidf_(b.z), sigmoidf_(b.w));
+            u = make_float4(a.x * s.x, a.y * s.y, a.z * s.z, a.w * s.w);
         }
-        U[idx] = u;
+        reinterpret_cast<float4*>(U)[idx] = u;
+        if (SG && r >= PADL && r < PADL + TT) reinterpret_cast<float4*>(SG)[(r - PADL) * C4 + c4] = s;
     }
 }
 
 __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __restrict__ g, SeqGeom sg, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out) {
-    __shared__ float U[ROWS * CH];
+    __shared__ __align__(16) float U[ROWS * CH];
     const int s = blockIdx.x, t0 = blockIdx.y * TT;
     const long base = seq_base(sg, s);
-    stage_glu(U, g, base, sg.tok_stride, t0, sg.L);
+    stage_glu(U, nullptr, g, base, sg.tok_stride, t0, sg.L);
     const int c = threadIdx.x % CH, half = threadIdx.x / CH;     // 2 halves x 16 tokens
     float wr[KS];
 #pragma unroll
@@ -60,9 +66,10 @@ __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ dz, SeqGeom sg,
                                                              const float* __restrict__ w, int seqs_per_block, float* __restrict__ dg,
                                                              float* __restrict__ dw, float* __restrict__ dbias) {
-    extern __shared__ float smem[];
-    float* U = smem;                 // [ROWS][CH]
-    float* DZ = smem + ROWS * CH;    // [ROWS][CH]
+    extern __shared__ __align__(16) float smem[];
+    float* U = smem;                    // [ROWS][CH]
+    float* DZ = smem + ROWS * CH;       // [ROWS][CH]
+    float* SG = DZ + ROWS * CH;         // [TT][CH]
     const int c = threadIdx.x % CH, half = threadIdx.x / CH;
     float wr[KS], dwr[KS];
 #pragma unroll
@@ -73,13 +80,17 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __rest
         const long base = seq_base(sg, s);
         for (int t0 = 0; t0 < sg.L; t0 += TT) {
             __syncthreads();
-            stage_glu(U, g, base, sg.tok_stride, t0, sg.L);
-            for (int idx = threadIdx.x; idx < ROWS * CH; idx += blockDim.x) {
-                int r = idx / CH, cc = idx % CH;
-                int tok = t0 - PADL + r;
-                DZ[idx] = (tok >= 0 && tok < sg.L) ? __ldg(dz + (base + (long)tok * sg.tok_stride) * CH + cc) : 0.f;
+            stage_glu(U, SG, g, base, sg.tok_stride, t0, sg.L);
+#pragma unroll 4
+            for (int idx = threadIdx.x; idx < ROWS * C4; idx += blockDim.x) {
+                const int r = idx / C4, c4 = idx % C4;
+                const int tok = t0 - PADL + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tok >= 0 && tok < sg.L) v = __ldg(reinterpret_cast<const float4*>(dz + (base + (long)tok * sg.tok_stride) * CH) + c4);
+                reinterpret_cast<float4*>(DZ)[idx] = v;
             }
             __syncthreads();
+#pragma unroll 2
             for (int tl = half * 16; tl < half * 16 + 16; ++tl) {
                 const int tok = t0 + tl;
                 if (tok >= sg.L) break;
@@ -93,10 +104,10 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __rest
                 for (int k = 0; k < KS; ++k) dwr[k] = fmaf(dzc, U[(tl + k) * CH + c], dwr[k]);
                 db += dzc;
                 const long row = base + (long)tok * sg.tok_stride;
-                const float a = __ldg(g + row * (2 * CH) + c);
-                const float sg_ = sigmoidf_(__ldg(g + row * (2 * CH) + CH + c));
+                const float sg_ = SG[tl * CH + c];
+                const float u = U[(tl + PADL) * CH + c];            // a * sigmoid(b)
                 dg[row * (2 * CH) + c] = du * sg_;
-                dg[row * (2 * CH) + CH + c] = du * a * sg_ * (1.f - sg_);
+                dg[row * (2 * CH) + CH + c] = du * u * (1.f - sg_);
             }
         }
     }
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __rest
 }  // namespace
 
 CMGAN_API int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* bias, int B, int T, int F, int axis, float* out, void* stream) {
-    CMGAN_REQUIRE(g && w && bias && out, "cmgan_glu_dwconv_fwd: null pointer");
+    CMGAN_REQUIRE(g && w && bias && out && (((uintptr_t)g) & 15) == 0, "cmgan_glu_dwconv_fwd: bad pointer");
     CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_glu_dwconv_fwd: bad axis");
     SeqGeom sg = make_seq_geom(B, T, F, axis);
     if (sg.n_seq == 0) return 0;
@@ -119,19 +130,19 @@ CMGAN_API int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* 
 
 CMGAN_API int cmgan_glu_dwconv_bwd(const float* g, const float* dz, const float* w, int B, int T, int F, int axis, float* dg, float* dw,
                                    float* dbias, void* stream) {
-    CMGAN_REQUIRE(g && dz && w && dg && dw && dbias, "cmgan_glu_dwconv_bwd: null pointer");
+    CMGAN_REQUIRE(g && dz && w && dg && dw && dbias && ((((uintptr_t)g) | ((uintptr_t)dz)) & 15) == 0, "cmgan_glu_dwconv_bwd: bad pointer");
     CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_glu_dwconv_bwd: bad axis");
     SeqGeom sg = make_seq_geom(B, T, F, axis);
     if (sg.n_seq == 0) return 0;
     static bool attr_set = false;
-    const int smem = 2 * ROWS * CH * (int)sizeof(float);
+    const int smem = (2 * ROWS + TT) * CH * (int)sizeof(float);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(glu_dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         CMGAN_REQUIRE(e == cudaSuccess, "cmgan_glu_dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    // enough blocks for ~4 waves of 148 SMs x 3 resident blocks, but at least one sequence per block
-    int spb = sg.n_seq / (148 * 3 * 4);
+    // enough blocks for ~4 waves of 148 SMs x 2 resident blocks, but at least one sequence per block
+    int spb = sg.n_seq / (148 * 2 * 4);
     if (spb < 1) spb = 1;
     glu_dwconv_bwd_kernel<<<cdiv(sg.n_seq, spb), 256, smem, (cudaStream_t)stream>>>(g, dz, sg, w, spb, dg, dw, dbias);
     return cmgan_check_launch("glu_dwconv_bwd_kernel");

@@ -92,7 +92,8 @@ __global__ void uncompress_bwd_kernel(const float* __restrict__ re_p, const floa
         dr = gr * (mp + mp2 * re * re) + gi * (mp2 * re * im);
         di = gr * (mp2 * re * im) + gi * (mp + mp2 * im * im);
     }
-    dre[i] = dr; dim_[i] = di;
+    if (accumulate) { dre[i] += dr; dim_[i] += di; }
+    else { dre[i] = dr; dim_[i] = di; }
 }
 
 // generic strided power law  Y = X * |X|^p  over a (d0, d1, d2) index space (power_compress p = -0.7, power_uncompress p = 7/3)

@@ -58,7 +58,7 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
 struct TcCfg { int BN, stages, tmem_cols, resident, ntiles; };
 
 template <bool ASYNC_A>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
+__global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
                                                                     const TcCfg cfg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
@@ -342,11 +342,13 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     cfg.resident = (long)nchunks * b_tile <= RESIDENT_MAX ? 1 : 0;
     const int fixed = 1024 /*alignment*/ + STG_BYTES + 256 /*barriers*/ + (cfg.resident ? nchunks * b_tile : 0);
     const int per_stage = A_STAGE_BYTES + (cfg.resident ? 0 : b_tile);
-    cfg.stages = (SMEM_LIMIT - fixed) / per_stage;
-    if (cfg.stages > 6) cfg.stages = 6;
-    if (cfg.stages < 2) return 1;
     cfg.tmem_cols = 64;
     while (cfg.tmem_cols < 2 * cfg.BN) cfg.tmem_cols <<= 1;
+    // two co-resident CTAs per SM (twice the loads in flight, epilogues overlap) when shared memory, TMEM and registers allow it
+    int ctas = (a->pro == CMGAN_PRO_NONE && cfg.tmem_cols <= 256 && fixed + 3 * per_stage <= SMEM_LIMIT / 2) ? 2 : 1;
+    cfg.stages = (SMEM_LIMIT / ctas - fixed) / per_stage;
+    if (cfg.stages > 6) cfg.stages = 6;
+    if (cfg.stages < 2) return 1;
     cfg.ntiles = cdiv(a->M, BM);
     const size_t smem = (size_t)fixed + (size_t)cfg.stages * per_stage;
     if (g_num_sms == 0) {
@@ -360,7 +362,7 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     long total = (long)nchunks * cfg.BN * KC;
     pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
     if (cmgan_check_launch("pack_b_kernel")) return -1;
-    const int grid = cfg.ntiles < g_num_sms ? cfg.ntiles : g_num_sms;
+    const int grid = cfg.ntiles < ctas * g_num_sms ? cfg.ntiles : ctas * g_num_sms;
     if (a->pro == CMGAN_PRO_NONE) gemm_rows_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(*a, a->ws, cfg);
     else gemm_rows_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(*a, a->ws, cfg);
     return cmgan_check_launch("gemm_rows_tc_kernel");

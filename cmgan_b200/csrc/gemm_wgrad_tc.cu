@@ -19,8 +19,8 @@ using namespace cmgan_tc;
 constexpr int RS = 32;               // rows per stage (= 4 MMAs of K = 8)
 constexpr int MO = 128;              // k values per tile = UMMA M
 constexpr int A_STAGE = RS * MO * 4; // 16 KB
-constexpr int NPROD = 128;
-constexpr int NTHREADS = 160;
+constexpr int NPROD = 256;            // 8 loader warps (warps 0-3 also run the epilogue)
+constexpr int NTHREADS = 288;
 constexpr uint32_t BLK = 4096;       // bytes between 32-wide M/N blocks (4 row groups x 1024)
 
 __device__ __forceinline__ void advance_row(const CmganGemmArgs& g, RowInfo& r, int by) {
@@ -56,29 +56,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr_addr, (uint32_t)tmem_cols);
+    if (warp == 8) tmem_alloc(tmem_ptr_addr, (uint32_t)tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ---------------- producers ----------------
-        // A: thread -> 16-byte chunk j of k block mi, rows rg*8 .. rg*8+7 of the stage
+        // A: thread -> 16-byte chunk j of k block mi, rows rg*4 .. rg*4+3 of the stage
         const int aj = tid & 7, ami = (tid >> 3) & 3, arg = tid >> 5;
         const int ak = k0 + ami * 32 + aj * 4;
         const bool ak_ok = ak < g.Cin;
-        uint32_t a_off[8];
+        uint32_t a_off[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a_off[i] = ami * BLK + arg * 1024 + i * 128 + ((((aj >> 1) ^ (i & 3)) << 5) | ((aj & 1) << 4));
-        RowInfo r0 = decode_row(g, (int)(mbeg + arg * 8));
+        for (int i = 0; i < 4; ++i) a_off[i] = ami * BLK + (arg * 4 + i) * 128 + ((((aj >> 1) ^ i) << 5) | ((aj & 1) << 4));
+        RowInfo r0 = decode_row(g, (int)(mbeg + arg * 4));
         ChunkParams cp;
         cp.a = cp.b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!A_ASYNC && ak_ok) load_chunk_params(g, ak, cp);
-        // D: chunks q = tid + 128 u,  u < NB/16
+        // D: chunks q = tid + 256 u,  u < NB/32
         const int cpr = NB / 4;
-        const int nd = NB / 16;
+        const int nd = NB / 32;
         const int LAG = stages >= 3 ? 2 : 1;
         constexpr bool ANY_ASYNC = A_ASYNC || D_ASYNC;
 
@@ -88,22 +88,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                 const uint32_t par = (uint32_t)((it / stages) & 1);
                 const long mrow = mbeg + (long)it * RS;
                 // ---- gather the 8 A rows of this thread (registers or addresses)
-                long arow[8];
+                long arow[4];
                 {
                     RowInfo r = r0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const long m = mrow + arg * 8 + i;
+                    for (int i = 0; i < 4; ++i) {
+                        const long m = mrow + arg * 4 + i;
                         r.ok = m < mend;
                         arow[i] = in_row_of(g, r, tap);
                         advance_row(g, r, 1);
                     }
                     advance_row(g, r0, RS);
                 }
-                float4 av[8];
+                float4 av[4];
                 if (!A_ASYNC) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (arow[i] >= 0 && ak_ok) {
                             av[i] = __ldg(reinterpret_cast<const float4*>(g.A + g.tap_off[tap] + arow[i] * g.lda + ak));
@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                         }
                     }
                 }
-                float4 dv[16];
+                float4 dv[8];
                 if (!D_ASYNC) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         if (u < nd) {
-                            const int q = tid + 128 * u;
+                            const int q = tid + 256 * u;
                             const int row = q / cpr, cc = q % cpr;
                             const long m = mrow + row;
                             dv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                 mbar_wait(empty_bar(s), par ^ 1u);
                 const uint32_t abase = sA + s * A_STAGE, dbase = sD + s * d_stage;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     if (A_ASYNC) {
                         const bool ok = arow[i] >= 0 && ak_ok;
                         cp_async16(abase + a_off[i], g.A + (ok ? g.tap_off[tap] + arow[i] * g.lda + ak : 0), ok ? 16u : 0u);
@@ -146,9 +146,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     if (u < nd) {
-                        const int q = tid + 128 * u;
+                        const int q = tid + 256 * u;
                         const int row = q / cpr, cc = q % cpr;
                         const uint32_t off = (uint32_t)(cc >> 3) * BLK + row * 128 + (((((cc & 7) >> 1) ^ (row & 3)) << 5) | ((cc & 1) << 4));
                         if (D_ASYNC) {
@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                 }
             }
         }
-        // ---------------- epilogue: dW tile += accumulator ----------------
+        // ---------------- epilogue: dW tile += accumulator (warps 0-3: one TMEM lane quarter each) ----------------
+        if (warp < 4) {
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int k = k0 + warp * 32 + lane;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
             }
         }
         tc_fence_before();
+        }
     } else {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
     }

@@ -182,36 +182,33 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ x, long ldx, co
     }
 }
 
-// backward pass 2.  dx = scale * (g - [train] (S1/n + xhat*S2/n));  also dgamma[c] += S2, dbeta[c] += S1 (block 0 only)
+// backward pass 2.  dx = scale * (g - [train] (S1/n + xhat*S2/n));  also dgamma[c] += S2, dbeta[c] += S1 (first chunk of each group)
+// Block = one chunk of rows of one group; thread = (row-subgroup, channel): the per-(group, channel) constants are loaded once.
 __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dact, long ldd,
-                                      long rows_per_group, int G, int C, int act, int use_batch_stats,
+                                      long rows_per_group, int C, int chunk, int act, int use_batch_stats,
                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                       const float* __restrict__ mean, const float* __restrict__ rstd, long tstride,
                                       const float* __restrict__ slope, const double* __restrict__ S,
                                       float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    long total = (long)G * rows_per_group * C;
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (long)G * C && dgamma) {   // one thread per (grp, c): fold the per-group sums into the parameter grads
-        int c = (int)(i % C);
-        atomicAdd(dgamma + c, (float)S[i * 2 + 1]);
-        atomicAdd(dbeta + c, (float)S[i * 2]);
+    const int grp = blockIdx.y;
+    const long r_beg = (long)blockIdx.x * chunk;
+    const long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
+    const int c = threadIdx.x % C, rg = threadIdx.x / C, nrg = blockDim.x / C;
+    if (rg >= nrg) return;
+    const long t = (long)grp * tstride + c;
+    const float sc = scale[t], sh = shift[t], mu = mean[t], rs = rstd[t];
+    const float a = act ? slope[c] : 1.f;
+    const double s1 = S[((long)grp * C + c) * 2], s2 = S[((long)grp * C + c) * 2 + 1];
+    if (blockIdx.x == 0 && rg == 0 && dgamma) { atomicAdd(dgamma + c, (float)s2); atomicAdd(dbeta + c, (float)s1); }
+    float m1 = 0.f, m2 = 0.f;
+    if (use_batch_stats) { m1 = (float)(s1 / (double)rows_per_group); m2 = (float)(s2 / (double)rows_per_group); }
+    const long rb = (long)grp * rows_per_group;
+    for (long r = r_beg + rg; r < r_end; r += nrg) {
+        const float v = __ldg(x + (rb + r) * ldx + c), d = __ldg(dact + (rb + r) * ldd + c);
+        const float z = v * sc + sh;
+        const float gq = (act && z < 0.f) ? d * a : d;
+        dx[(rb + r) * lddx + c] = sc * (gq - m1 - (v - mu) * rs * m2);
     }
-    if (i >= total) return;
-    int c = (int)(i % C);
-    long row = i / C;
-    int grp = (int)(row / rows_per_group);
-    long t = (long)grp * tstride + c;
-    float sc = scale[t], sh = shift[t], mu = mean[t], rs = rstd[t];
-    float v = __ldg(x + row * ldx + c), d = __ldg(dact + row * ldd + c);
-    float z = v * sc + sh;
-    float gq = (act && z < 0.f) ? d * slope[c] : d;
-    float o = gq;
-    if (use_batch_stats) {
-        double inv_n = 1.0 / (double)rows_per_group;
-        float m1 = (float)(S[((long)grp * C + c) * 2] * inv_n), m2 = (float)(S[((long)grp * C + c) * 2 + 1] * inv_n);
-        o = gq - m1 - (v - mu) * rs * m2;
-    }
-    dx[row * lddx + c] = sc * o;
 }
 
 // y[row, c] = act(x*scale+shift) materialised (used where the consumer is not a GEMM with a prologue)
@@ -334,11 +331,13 @@ CMGAN_API int cmgan_norm_bwd_apply(const float* x, long long ldx, const float* d
                                    const float* rstd, long long tstride, const float* slope, const double* S, float* dx,
                                    long long lddx, float* dgamma, float* dbeta, void* stream) {
     CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S && dx, "cmgan_norm_bwd_apply: null pointer");
-    long total = (long)G * rows_per_group * C;
-    if (total == 0) return 0;
-    norm_bwd_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, G, C, act, use_batch_stats,
-                                                                             scale, shift, mean, rstd, tstride, slope, S, dx, lddx,
-                                                                             dgamma, dbeta);
+    CMGAN_REQUIRE(C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_bwd_apply: C=%d unsupported", C);
+    if (G == 0 || rows_per_group == 0) return 0;
+    const int nrg = 256 / C;
+    const int chunk = nrg * 32;
+    dim3 grid(cdiv(rows_per_group, chunk), G);
+    norm_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, C, chunk, act, use_batch_stats, scale, shift,
+                                                                 mean, rstd, tstride, slope, S, dx, lddx, dgamma, dbeta);
     return cmgan_check_launch("norm_bwd_apply_kernel");
 }
 
