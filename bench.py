@@ -194,21 +194,15 @@ def run_ours(args):
     B = args.batch
     torch.manual_seed(0)
     model = cmgan_b200.TSCNet(64, 201).to(dev).train()
-    flat = model.enable_flat_grads()
-    if world > 1:       # rank-0 parameters win, as DDP's constructor does (train.py:68)
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
+    from cmgan_b200.trainer import FusedTrainer
+    from cmgan_b200 import parallel
+    trainer = FusedTrainer(model, None)          # flat parameter/gradient buffers; rank-0 parameters win (train.py:68)
+    flat = trainer.gg
     clean, noisy = synth_batch(B, 1000 + rank, device=dev)
     hclean, hnoisy = synth_batch(B, 1000 + rank, pin=True)
 
-    def step(c, n):
-        call("cmgan_fill", flat, flat.numel(), 0.0)
-        go = training.forward_generator_step(model, c, n)
-        loss = training.generator_loss(go, c)
-        loss.backward()
-        if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        return loss
+    def step(c, n):          # eager: every kernel launched from Python
+        return trainer.generator_step(c, n, update=False)
 
     def barrier():
         if world > 1:
@@ -224,7 +218,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(K):
             fn()
-        host_ms[0] = (time.perf_counter() - t0) * 1e3 / K       # host time to enqueue one step (Python + launches)
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / K       # host time to enqueue one step
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -236,45 +230,66 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(clean, noisy)
+    ms_eager = timed(lambda: step(clean, noisy), args.steps)
+    eager_host_ms = host_ms[0]
+    # ---- the whole step as one CUDA graph (the gradient all-reduce stays an eager NCCL call when N > 1)
+    l0 = ops.LAUNCHES
+    trainer.capture_generator_step(clean, noisy, update=False, allreduce=False)
+    launches_per_step = (ops.LAUNCHES - l0) // 3           # 2 warm-up passes + 1 capture pass
+
+    def gstep(c, n):
+        loss = trainer.replay_generator_step(c, n)
+        if world > 1:
+            parallel.allreduce_mean_(flat)
+        return loss
+
+    for _ in range(3):
+        gstep(clean, noisy)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ops.LAUNCHES
-    ms = timed(lambda: step(clean, noisy), args.steps)
-    launches = ops.LAUNCHES - l0
+    ms = timed(lambda: gstep(clean, noisy), args.steps)
+    launches = launches_per_step * args.steps
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end: pinned host buffers in, loss scalar out, every step
-    dclean, dnoisy = torch.empty_like(clean), torch.empty_like(noisy)
     host_loss = torch.empty(1).pin_memory()
 
     def e2e_step():
-        dclean.copy_(hclean, non_blocking=True)
-        dnoisy.copy_(hnoisy, non_blocking=True)
-        loss = step(dclean, dnoisy)
+        loss = gstep(hclean, hnoisy)                     # H2D copies of the pinned batch into the graph's input buffers
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the loss every step (train.py:205)
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
-    # ---- forward only (configs[1]: eval forward, batch 4)
+    # ---- forward only (configs[1]: eval forward, batch 4), also as a CUDA graph
     model.eval()
     with torch.no_grad():
         def fwd_only():
             go = training.forward_generator_step(model, clean, noisy)
             return go["est_audio"]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fwd_only()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        fgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fgraph):
+            fwd_out = fwd_only()
         for _ in range(2):
-            fwd_only()
-        ms_f = timed(fwd_only, args.steps)
+            fgraph.replay()
+        ms_f = timed(fgraph.replay, args.steps)
     fwd_value = world * B * args.steps / (ms_f * 1e-3)
     model.train()
 
     # ---- dominant kernel: CUDA events around every GEMM launch of one instrumented step
     ops.PROBE = []
-    step(clean, noisy)
+    step(clean, noisy)          # eager pass: CUDA events cannot sit inside the captured graph
     torch.cuda.synchronize()
     probe, ops.PROBE = ops.PROBE, None
     if os.environ.get("CMGAN_PROBE_DUMP") and rank == 0:      # per-launch GEMM timings for analysis (not part of the JSON line)
@@ -301,9 +316,11 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(B), "global_batch": B * world, "clip_samples": CLIP, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
-                       "weights": "torch.manual_seed(0) default init"},
+                       "weights": "torch.manual_seed(0) default init", "launch": "one CUDA graph per step (cmgan_b200.trainer.FusedTrainer)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * CLIP * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "eager": {"value": world * B * args.steps / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager / args.steps,
+                      "host_enqueue_ms_per_step": eager_host_ms, "note": "same step launched kernel by kernel from Python (no CUDA graph)"},
             "clocks": clocks,
             "roofline": roofline,
             "forward_only": {"value": fwd_value, "unit": UNIT, "ms_per_step": ms_f / args.steps, "workload": f"configs[1]: eval forward, batch {B} x 2 s"},

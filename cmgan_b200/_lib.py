@@ -39,6 +39,7 @@ class GemmArgs(ctypes.Structure):
         ("precision", ctypes.c_int),
         ("ws", ctypes.c_void_p), ("ws_floats", ctypes.c_longlong),
         ("C2", ctypes.c_void_p), ("ldc2", ctypes.c_longlong),
+        ("seed_dev", ctypes.c_void_p),
     ]
 
 

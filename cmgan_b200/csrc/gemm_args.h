@@ -55,4 +55,5 @@ typedef struct CmganGemmArgs {
     int precision;             // 0 = fp32 FFMA, 1 = tf32 tcgen05 tensor cores (shapes the tensor path does not cover fall back to fp32 FFMA)
     float* ws; long long ws_floats;   // tf32 path: scratch for the re-tiled weight operand, >= N_pad * Cin * ntaps floats (caller-owned)
     float* C2; long long ldc2;        // second output of CMGAN_EPI_SWISH_DUAL
+    const unsigned long long* seed_dev;   // optional device counter added to both dropout seeds (CUDA-graph replays draw fresh masks)
 } CmganGemmArgs;

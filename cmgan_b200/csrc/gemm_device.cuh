@@ -6,6 +6,10 @@
 
 namespace cmgan_gemm {
 
+// dropout seeds: the per-site constant plus an optional device-resident step counter
+__device__ __forceinline__ unsigned long long eff_seed(const CmganGemmArgs& g) { return g.seed + (g.seed_dev ? __ldg(g.seed_dev) : 0ull); }
+__device__ __forceinline__ unsigned long long eff_pro_seed(const CmganGemmArgs& g) { return g.pro_seed + (g.seed_dev ? __ldg(g.seed_dev) : 0ull); }
+
 struct RowInfo { int b, y, x; bool ok; };
 
 __device__ __forceinline__ RowInfo decode_row(const CmganGemmArgs& g, int m) {
@@ -34,9 +38,9 @@ __device__ __forceinline__ long in_row_of(const CmganGemmArgs& g, const RowInfo&
 __device__ __forceinline__ float apply_pro(const CmganGemmArgs& g, float a, long r, int k, float mean, float rstd) {
     switch (g.pro) {
         case CMGAN_PRO_LN: return (a - mean) * rstd * __ldg(g.p1 + k) + __ldg(g.p2 + k);
-        case CMGAN_PRO_SWISH_DROP: return swishf_(a) * cmgan_drop_scale(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
+        case CMGAN_PRO_SWISH_DROP: return swishf_(a) * cmgan_drop_scale(eff_pro_seed(g), (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
         case CMGAN_PRO_BN_SWISH: return swishf_(a * __ldg(g.p0 + k) + __ldg(g.p1 + k));
-        case CMGAN_PRO_DROP: return a * g.pro_alpha * cmgan_drop_scale(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
+        case CMGAN_PRO_DROP: return a * g.pro_alpha * cmgan_drop_scale(eff_pro_seed(g), (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep);
         case CMGAN_PRO_IN_PRELU: {
             long b = r / g.rows_per_batch;
             float z = a * __ldg(g.p0 + b * g.pstride + k) + __ldg(g.p1 + b * g.pstride + k);
@@ -71,13 +75,13 @@ __device__ __forceinline__ void load_a4(const CmganGemmArgs& g, long r, int tap,
 __device__ __forceinline__ float epilogue(const CmganGemmArgs& g, float v, long m, int n, const float* cptr) {
     switch (g.epi) {
         case CMGAN_EPI_DROP_RES: {
-            float o = g.alpha * v * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+            float o = g.alpha * v * cmgan_drop_scale(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
             if (g.R) o += __ldg(g.R + m * g.ldr + n);
             return o;
         }
         case CMGAN_EPI_DSWISH_DROP: {
             float h = __ldg(g.aux + m * g.ldaux + n);
-            return v * dswishf_(h) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+            return v * dswishf_(h) * cmgan_drop_scale(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
         }
         case CMGAN_EPI_DBNSWISH: {
             float z = __ldg(g.aux + m * g.ldaux + n) * __ldg(g.e0 + n) + __ldg(g.e1 + n);
@@ -111,14 +115,14 @@ __device__ __forceinline__ float4 transform4(const CmganGemmArgs& g, float4 v, l
             v.x = swishf_(v.x); v.y = swishf_(v.y); v.z = swishf_(v.z); v.w = swishf_(v.w);
             if (g.pro_thr) {
                 float ds[4];
-                cmgan_drop_scale4(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep, ds);
+                cmgan_drop_scale4(eff_pro_seed(g), (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep, ds);
                 v.x *= ds[0]; v.y *= ds[1]; v.z *= ds[2]; v.w *= ds[3];
             }
             break;
         }
         case CMGAN_PRO_DROP: {
             float ds[4];
-            cmgan_drop_scale4(g.pro_seed, (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep, ds);
+            cmgan_drop_scale4(eff_pro_seed(g), (uint64_t)r * g.Cin + k, g.pro_thr, g.pro_inv_keep, ds);
             v.x *= g.pro_alpha * ds[0]; v.y *= g.pro_alpha * ds[1]; v.z *= g.pro_alpha * ds[2]; v.w *= g.pro_alpha * ds[3];
             break;
         }
@@ -155,14 +159,14 @@ __device__ __forceinline__ void epilogue4(const CmganGemmArgs& g, float v[4], lo
     switch (g.epi) {
         case CMGAN_EPI_DROP_RES: {
             float ds[4];
-            cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, ds);
+            cmgan_drop_scale4(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, ds);
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = g.alpha * v[j] * ds[j] + (g.R ? x[j] : 0.f);
             break;
         }
         case CMGAN_EPI_DSWISH_DROP: {
             float ds[4];
-            cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, ds);
+            cmgan_drop_scale4(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, ds);
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(x[j]) * ds[j];
             break;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_rows_kernel(const __grid_constant_
             if (n >= g.N) continue;
             float v = acc[i][j] + (g.bias ? __ldg(g.bias + n) : 0.f);
             if (g.epi == CMGAN_EPI_SWISH_DUAL) {
-                g.C2[m * g.ldc2 + n] = swishf_(v) * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+                g.C2[m * g.ldc2 + n] = swishf_(v) * cmgan_drop_scale(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
                 if (g.C) g.C[m * g.ldc + n] = v;
             } else {
                 float* cp = g.C + m * g.ldc + n;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_wgrad_kernel(const __grid_constant
             float d = 0.f;
             if (m < mend && n < g.N) {
                 d = __ldg(g.D + m * g.ldd + n);
-                if (g.prod == 1) d *= g.alpha * cmgan_drop_scale(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
+                if (g.prod == 1) d *= g.alpha * cmgan_drop_scale(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep);
             }
             rd[j] = d;
         }

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
                             if (g.epi == CMGAN_EPI_SWISH_DUAL) {
                                 if (g.C) *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
                                 float o[4];
-                                cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, o);
+                                cmgan_drop_scale4(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, o);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) o[j] *= swishf_(vv[j]);
                                 *reinterpret_cast<float4*>(g.C2 + m * g.ldc2 + n) = make_float4(o[0], o[1], o[2], o[3]);

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                                 dv[u] = __ldg(reinterpret_cast<const float4*>(g.D + m * g.ldd + cc * 4));
                                 if (g.prod == 1) {
                                     float ds[4];
-                                    cmgan_drop_scale4(g.seed, (uint64_t)m * g.N + cc * 4, g.drop_thr, g.inv_keep, ds);
+                                    cmgan_drop_scale4(eff_seed(g), (uint64_t)m * g.N + cc * 4, g.drop_thr, g.inv_keep, ds);
                                     dv[u].x *= g.alpha * ds[0]; dv[u].y *= g.alpha * ds[1]; dv[u].z *= g.alpha * ds[2]; dv[u].w *= g.alpha * ds[3];
                                 }
                             }
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
 
 // dbias[n] += sum_m prod(D[m, n])
 __global__ void colsum_kernel(const float* __restrict__ D, long ldd, long M, int N, int prod, float alpha, unsigned long long seed, unsigned thr,
-                              float inv_keep, int rows_per_block, float* __restrict__ out) {
+                              float inv_keep, int rows_per_block, float* __restrict__ out, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += __ldg(seed_dev);
     __shared__ float sm[256];
     const int c = threadIdx.x % N, rg = threadIdx.x / N, nrg = blockDim.x / N;
     const long r_beg = (long)blockIdx.x * rows_per_block;
@@ -297,7 +298,7 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     if (rc) return rc;
     if (a->dbias) {
         const int rpb = 64 * (256 / a->N > 0 ? 256 / a->N : 1);     // ~64 rows per thread -> thousands of blocks
-        colsum_kernel<<<cdiv(a->M, rpb), 256, 0, st>>>(a->D, a->ldd, a->M, a->N, a->prod, a->alpha, a->seed, a->drop_thr, a->inv_keep, rpb, a->dbias);
+        colsum_kernel<<<cdiv(a->M, rpb), 256, 0, st>>>(a->D, a->ldd, a->M, a->N, a->prod, a->alpha, a->seed, a->drop_thr, a->inv_keep, rpb, a->dbias, a->seed_dev);
         return cmgan_check_launch("colsum_kernel");
     }
     return 0;

@@ -154,16 +154,19 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __
 
 // y = prelu(x * drop(i), slope[c])   (Dropout(0.3) then PReLU(64), discriminator.py:55-56); in place allowed
 __global__ void drop_prelu_kernel(const float* __restrict__ x, long n, int C, const float* __restrict__ slope, unsigned long long seed,
-                                  unsigned thr, float inv_keep, float* __restrict__ y) {
+                                  unsigned thr, float inv_keep, float* __restrict__ y, const unsigned long long* __restrict__ seed_dev) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (seed_dev) seed += __ldg(seed_dev);
     float z = x[i] * cmgan_drop_scale(seed, (uint64_t)i, thr, inv_keep);
     y[i] = z >= 0.f ? z : z * slope[i % C];
 }
 __global__ void drop_prelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, long n, int C, const float* __restrict__ slope,
-                                      unsigned long long seed, unsigned thr, float inv_keep, float* __restrict__ dx, float* __restrict__ dslope) {
+                                      unsigned long long seed, unsigned thr, float inv_keep, float* __restrict__ dx, float* __restrict__ dslope,
+                                      const unsigned long long* __restrict__ seed_dev) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (seed_dev) seed += __ldg(seed_dev);
     float ds = cmgan_drop_scale(seed, (uint64_t)i, thr, inv_keep);
     float z = x[i] * ds;
     float g = dy[i];
@@ -188,7 +191,16 @@ __global__ void lsigmoid_bwd_kernel(const float* __restrict__ x, const float* __
     if ((threadIdx.x & 31) == 0 && p != 0.f) atomicAdd(dslope, p);
 }
 
+__global__ void counter_add_kernel(unsigned long long* p, unsigned long long v) { *p += v; }
+
 }  // namespace
+
+// *p += v on the device (step counters that CUDA-graph replays advance)
+CMGAN_API int cmgan_counter_add(unsigned long long* p, unsigned long long v, void* stream) {
+    CMGAN_REQUIRE(p != nullptr, "cmgan_counter_add: null pointer");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p, v);
+    return cmgan_check_launch("counter_add_kernel");
+}
 
 // out[i] = 1 if element i is kept by dropout(seed, p) else 0  (tests: feed the exact masks to the oracle)
 CMGAN_API int cmgan_dropout_mask(float* out, long long n, unsigned long long seed, unsigned int thr, void* stream) {
@@ -245,18 +257,18 @@ CMGAN_API int cmgan_maxpool_bwd(const float* dout, const int* arg, int B, long l
 }
 
 CMGAN_API int cmgan_drop_prelu(const float* x, long long n, int C, const float* slope, unsigned long long seed, unsigned int thr, float inv_keep,
-                               float* y, void* stream) {
+                               float* y, const unsigned long long* seed_dev, void* stream) {
     CMGAN_REQUIRE(x && slope && y, "cmgan_drop_prelu: null pointer");
     if (n == 0) return 0;
-    drop_prelu_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, C, slope, seed, thr, inv_keep, y);
+    drop_prelu_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, C, slope, seed, thr, inv_keep, y, seed_dev);
     return cmgan_check_launch("drop_prelu_kernel");
 }
 
 CMGAN_API int cmgan_drop_prelu_bwd(const float* x, const float* dy, long long n, int C, const float* slope, unsigned long long seed,
-                                   unsigned int thr, float inv_keep, float* dx, float* dslope, void* stream) {
+                                   unsigned int thr, float inv_keep, float* dx, float* dslope, const unsigned long long* seed_dev, void* stream) {
     CMGAN_REQUIRE(x && dy && slope && dx && dslope, "cmgan_drop_prelu_bwd: null pointer");
     if (n == 0) return 0;
-    drop_prelu_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, C, slope, seed, thr, inv_keep, dx, dslope);
+    drop_prelu_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, C, slope, seed, thr, inv_keep, dx, dslope, seed_dev);
     return cmgan_check_launch("drop_prelu_bwd_kernel");
 }
 

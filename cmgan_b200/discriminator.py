@@ -78,7 +78,7 @@ def disc_fwd(x, y, P, training: bool, seed: int, save):
     gemm(A=pooled, lda=n0, W=w14, sb_k=1, sb_n=n0, bias=P["layers.14.bias"], C=h1, ldc=n1, M=B, N=n1, Cin=n0, precision=0)
     a1 = _empty(B, n1, dev=dev)
     thr, inv = ops.drop_params(DROP_P if training else 0.0)
-    call("cmgan_drop_prelu", h1, B * n1, n1, P["layers.16.weight"], seed, thr, inv, a1)
+    call("cmgan_drop_prelu", h1, B * n1, n1, P["layers.16.weight"], seed, thr, inv, a1, ops.SEED_DEV)
     w17, s17 = _spectral(P, "layers.17", training, dev)
     h2 = _empty(B, 1, dev=dev)
     gemm(A=a1, lda=n1, W=w17, sb_k=1, sb_n=n1, bias=P["layers.17.bias"], C=h2, ldc=1, M=B, N=1, Cin=n1, precision=0)
@@ -126,7 +126,7 @@ def disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
     da1 = _empty(B, n1, dev=dev)
     gemm(A=dh2, lda=1, W=S["w17"], sb_k=n1, sb_n=1, C=da1, ldc=n1, M=B, N=n1, Cin=1, precision=0)
     dh1 = _empty(B, n1, dev=dev)
-    call("cmgan_drop_prelu_bwd", S["h1"], da1, B * n1, n1, P["layers.16.weight"], S["seed"], S["thr"], S["inv"], dh1, G["layers.16.weight"])
+    call("cmgan_drop_prelu_bwd", S["h1"], da1, B * n1, n1, P["layers.16.weight"], S["seed"], S["thr"], S["inv"], dh1, G["layers.16.weight"], ops.SEED_DEV)
     dw14 = torch.zeros_like(S["w14"])
     gemm(wgrad=True, A=S["pooled"], lda=n0, Cin=n0, D=dh1, ldd=n1, N=n1, W=None, C=dw14, sb_k=1, sb_n=n0, ldc=0, M=B, dbias=G["layers.14.bias"],
          precision=0)

@@ -17,6 +17,7 @@ from ._lib import GemmArgs, MAX_TAPS, lib
 _KERNELS = {"cmgan_attention_bwd": 3}
 LAUNCHES = 0
 PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" else 0   # default for every dense contraction
+SEED_DEV = None  # optional uint64 device counter added to every dropout seed (set by the trainer for CUDA-graph replay)
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
 PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
@@ -103,6 +104,7 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
     a.pro_thr, a.pro_inv_keep = drop_params(pro_drop_p)
     a.D, a.ldd, a.prod, a.dbias = ptr(D), ldd, prod, ptr(dbias)
     a.C2, a.ldc2 = ptr(C2), ldc2
+    a.seed_dev = ptr(SEED_DEV)
     a.precision = PRECISION if precision is None else precision
     ws = None
     if a.precision == 1 and not wgrad and N % 16 == 0 and N <= 256 and Cin % 32 == 0:

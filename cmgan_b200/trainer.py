@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-from . import parallel, signal
+from . import ops, parallel, signal
 from .discriminator import Discriminator, disc_bwd, disc_fwd
 from .generator import TSCNet
 from .network import tscnet_bwd, tscnet_fwd
@@ -40,10 +40,12 @@ class _Adam:
         self.p, self.g = flat_p, flat_g
         self.m, self.v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
         self.lr, self.betas, self.eps, self.wd, self.t = lr, betas, eps, wd, 0
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=flat_p.device)      # device-side step count (CUDA-graph replay safe)
 
     def step(self):
         self.t += 1
-        call("cmgan_adamw", self.p, self.g, self.m, self.v, self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t)
+        call("cmgan_counter_add", self.t_dev, 1)
+        call("cmgan_adamw", self.p, self.g, self.m, self.v, self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t, self.t_dev)
 
 
 class FusedTrainer:
@@ -60,13 +62,18 @@ class FusedTrainer:
             parallel.broadcast_module(disc)
         self.seed, self.step_no = seed, 0
         self.last = None
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.pg.device)   # added to every dropout seed on the device
+        self._graph = None
 
-    def generator_step(self, clean: torch.Tensor, noisy: torch.Tensor, update: bool = True) -> torch.Tensor:
+    def generator_step(self, clean: torch.Tensor, noisy: torch.Tensor, update: bool = True, allreduce: bool = True) -> torch.Tensor:
         """train.py:179-193.  clean / noisy: (B, L) un-normalised waveforms on the GPU.  Returns the loss (device scalar)."""
         m, dev = self.model, clean.device
-        self.step_no += 1
+        if self._graph is None or torch.cuda.is_current_stream_capturing():
+            self.step_no += 1
         seed = self.seed * 7919 + self.step_no
         B, L = noisy.shape
+        ops.SEED_DEV = self.step_dev
+        call("cmgan_counter_add", self.step_dev, 1)
         call("cmgan_fill", self.gg, self.gg.numel(), 0.0)
         c = signal.rms_scale(noisy)
         noisy_spec = signal.stft_compress(noisy, c).permute(0, 1, 3, 2)           # (B,2,T,F)
@@ -101,7 +108,9 @@ class FusedTrainer:
             call("cmgan_gen_loss_finalize", acc, float(n), float(B * Lo), self.w[0], self.w[1], self.w[2], 0.0, None, B, loss, None)
         signal.uncompress_istft_bwd(fr, fi, d_audio, d_er, d_ei, True)
         tscnet_bwd(S, d_er, d_ei, P, m._flat_views)
-        parallel.allreduce_mean_(self.gg)
+        ops.SEED_DEV = None
+        if allreduce:
+            parallel.allreduce_mean_(self.gg)
         if update:
             self.opt_g.step()
         self.last = dict(clean_mag=clean_mag, est_mag=est_mag, est_audio=est_audio, B=B)
@@ -111,6 +120,7 @@ class FusedTrainer:
         """train.py:161-170,199-201 once the PESQ targets exist: MSE(D(c,c),1) + MSE(D(c, est.detach()), target)."""
         d, L = self.disc, self.last
         dev = pesq_target.device
+        ops.SEED_DEV = self.step_dev
         Pd = d._tensor_dict()
         call("cmgan_fill", self.gd, self.gd.numel(), 0.0)
         cm, em = L["clean_mag"].permute(0, 1, 3, 2), L["est_mag"].permute(0, 1, 3, 2)
@@ -123,7 +133,32 @@ class FusedTrainer:
         call("cmgan_disc_loss", d_max, d_enh, pesq_target, L["B"], loss, g_max, g_enh)
         disc_bwd(s1, g_enh, Pd, d._flat_views, False, False)
         disc_bwd(s2, g_max, Pd, d._flat_views, False, False)
+        ops.SEED_DEV = None
         parallel.allreduce_mean_(self.gd)
         if update:
             self.opt_d.step()
         return loss
+
+    # ------------------------------------------------------------------ CUDA graph of the generator step
+    def capture_generator_step(self, clean: torch.Tensor, noisy: torch.Tensor, update: bool = True, allreduce: bool = True) -> None:
+        """Record ``generator_step`` once into a CUDA graph (all ~500 kernel launches, the NCCL all-reduce and AdamW); afterwards
+        ``replay_generator_step`` costs two H2D/D2D copies and one graph launch on the host.  Dropout masks and Adam bias
+        corrections stay fresh across replays because seeds / step counts are read from device counters."""
+        self.static_clean, self.static_noisy = clean.clone(), noisy.clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.generator_step(self.static_clean, self.static_noisy, update, allreduce)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.static_loss = self.generator_step(self.static_clean, self.static_noisy, update, allreduce)
+
+    def replay_generator_step(self, clean: torch.Tensor, noisy: torch.Tensor) -> torch.Tensor:
+        self.static_clean.copy_(clean, non_blocking=True)
+        self.static_noisy.copy_(noisy, non_blocking=True)
+        self._graph.replay()
+        return self.static_loss

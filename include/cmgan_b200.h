@@ -74,8 +74,8 @@ int cmgan_spectral_norm(const float* W, int R, int Cc, float* u, float* v, int t
 int cmgan_spectral_norm_bwd(const float* w_sn, const float* dw_sn, int R, int Cc, const float* u, const float* v, const float* sigma, float* dW, void* stream);
 int cmgan_norm_maxpool(const float* x, int B, long long rows, int C, const float* scale, const float* shift, const float* slope, float* out, int* arg, void* stream);
 int cmgan_maxpool_bwd(const float* dout, const int* arg, int B, long long rows, int C, float* dact, void* stream);
-int cmgan_drop_prelu(const float* x, long long n, int C, const float* slope, unsigned long long seed, unsigned int thr, float inv_keep, float* y, void* stream);
-int cmgan_drop_prelu_bwd(const float* x, const float* dy, long long n, int C, const float* slope, unsigned long long seed, unsigned int thr, float inv_keep, float* dx, float* dslope, void* stream);
+int cmgan_drop_prelu(const float* x, long long n, int C, const float* slope, unsigned long long seed, unsigned int thr, float inv_keep, float* y, const unsigned long long* seed_dev, void* stream);
+int cmgan_drop_prelu_bwd(const float* x, const float* dy, long long n, int C, const float* slope, unsigned long long seed, unsigned int thr, float inv_keep, float* dx, float* dslope, const unsigned long long* seed_dev, void* stream);
 int cmgan_lsigmoid(const float* x, long long n, const float* slope, float* y, void* stream);
 int cmgan_lsigmoid_bwd(const float* x, const float* y, const float* dy, long long n, const float* slope, float* dx, float* dslope, void* stream);
 
@@ -85,7 +85,8 @@ int cmgan_time_loss(const float* ea, long long lde, const float* clean, long lon
 int cmgan_gen_loss_finalize(const double* acc, double n_spec, double n_time, float w_ri, float w_mag, float w_t, float w_gan, const float* fake, int B, float* loss, float* d_fake, void* stream);
 int cmgan_disc_loss(const float* d_max, const float* d_enh, const float* target, int B, float* loss, float* g_max, float* g_enh, void* stream);
 int cmgan_mag_bwd_add(const float* er, const float* ei, const float* d_mag, long long gb, long long gt, long long gf, int B, int T, int F, float* d_er, float* d_ei, void* stream);
-int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd, int step, void* stream);
+int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd, int step, const unsigned long long* step_dev, void* stream);
+int cmgan_counter_add(unsigned long long* p, unsigned long long v, void* stream);
 
 #ifdef __cplusplus
 }
