@@ -32,10 +32,11 @@ constexpr int BM = 128;              // rows per tile = UMMA M
 constexpr int KC = 32;               // floats per K chunk = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * KC * 4;   // 16 KB
 constexpr int NPROD = 128;           // producer threads (warps 0-3)
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS4 = 320, NTHREADS8 = 448;     // 4 or 8 epilogue warps
 constexpr int SLAB = 64;             // epilogue column slab
 constexpr int STG_LD = SLAB + 4;     // staging row stride (floats): conflict-free 128-bit accesses
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;      // 34816
+constexpr int STG_BYTES4 = 4 * 32 * STG_LD * 4;     // 34816: per-warp staging of 32 rows x (64 + 4) floats
+constexpr int STG_BYTES8 = 8 * 32 * STG_LD * 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int RESIDENT_MAX = 96 * 1024;
 
@@ -57,8 +58,8 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
 
 struct TcCfg { int BN, stages, tmem_cols, resident, ntiles; };
 
-template <bool ASYNC_A>
-__global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
+template <bool ASYNC_A, bool EPI8>
+__global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI8) ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
                                                                     const TcCfg cfg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
     const uint32_t sB = sA + stages * A_STAGE_BYTES;
     const uint32_t b_region = (uint32_t)(cfg.resident ? nchunks : stages) * b_tile_bytes;
     const uint32_t sStg = sB + b_region;
-    const uint32_t bars = sStg + STG_BYTES;
+    const uint32_t bars = sStg + (EPI8 ? STG_BYTES8 : STG_BYTES4);
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (stages + s); };
     const uint32_t tfull_bar = bars + 8u * (2 * stages);          // [2]
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), NPROD + (cfg.resident ? 0 : 1)); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8u * b, 1); mbar_init(tempty_bar + 8u * b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8u * b, 1); mbar_init(tempty_bar + 8u * b, EPI8 ? 8 : 4); }
         mbar_init(bready_bar, 1);
         fence_barrier_init();
     }
@@ -239,19 +240,28 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
         }
         __syncwarp();
     } else {
-        // ================================ epilogue (warps 6-9) ================================
-        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
-        float* stg = reinterpret_cast<float*>(base_ptr + (sStg - base)) + (warp - 6) * 32 * STG_LD;
-        const int col4 = (lane & 15) * 4;          // this lane's 4 columns within the slab
-        const int rsub = lane >> 4;                // 0/1: two rows per pass
+        // ================================ epilogue (warps 6-9, or 6-13 with EPI8) ================================
+        // a warp may only touch its TMEM lane quarter (warp % 4); with EPI8 two warps share a quarter and split the column slabs
+        const int q4 = warp & 3;
+        const int ew = warp - 6;
+        const int half = ew >> 2, nhalf = EPI8 ? 2 : 1;
+        const int W = EPI8 ? max(16, min(SLAB, BN / 2)) : SLAB;          // slab width (columns)
+        const int lpr = W / 4;                                           // lanes per row (float4 each)
+        const int rpp = 32 / lpr;                                        // rows per pass
+        float* stg = reinterpret_cast<float*>(base_ptr + (sStg - base)) + ew * 32 * STG_LD;
+        const int col4 = (lane % lpr) * 4;
+        const int rsub = lane / lpr;
+        const int nslabs = (BN + W - 1) / W;
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int buf = lt & 1;
             const int m0 = (blockIdx.x + lt * gridDim.x) * BM;
             mbar_wait(tfull_bar + 8u * buf, (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * acc_stride + ((uint32_t)(q4 * 32) << 16);
-            for (int n0 = 0; n0 < BN; n0 += SLAB) {
-                const int ncols = min(SLAB, BN - n0);
+            bool released = false;
+            for (int sl = half; sl < nslabs; sl += nhalf) {
+                const int n0 = sl * W;
+                const int ncols = min(W, BN - n0);
                 for (int q = 0; q < ncols; q += 16) {
                     float acc[16];
                     tmem_ld16(trow + (uint32_t)(n0 + q), acc);
@@ -259,10 +269,11 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4*>(stg + lane * STG_LD + q + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
                 }
-                if (n0 + SLAB >= BN) {                        // last slab read: the accumulator buffer may be overwritten
+                if (sl + nhalf >= nslabs) {                   // this warp's last slab is out of TMEM: the accumulator buffer may be overwritten
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar + 8u * buf);
+                    released = true;
                 }
                 __syncwarp();
                 const int n = n0 + col4;
@@ -271,19 +282,20 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
                     if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
                     if (g.epi == CMGAN_EPI_DBNSWISH) { e0v = __ldg(reinterpret_cast<const float4*>(g.e0 + n)); e1v = __ldg(reinterpret_cast<const float4*>(g.e1 + n)); }
                     const bool extra = epi_needs_extra(g);
-                    for (int rb = 0; rb < 32; rb += 16) {          // 8 row pairs per batch: issue all auxiliary loads first
+                    for (int rb = 0; rb < 32; rb += 8 * rpp) {     // 8 passes per batch: issue all auxiliary loads first
                         float4 ex[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const long m = (long)m0 + q4 * 32 + rb + 2 * u + rsub;
+                            const int rl = rb + u * rpp + rsub;
+                            const long m = (long)m0 + q4 * 32 + rl;
                             ex[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (extra && m < g.M) ex[u] = __ldg(reinterpret_cast<const float4*>(epi_extra_ptr(g, m, n)));
+                            if (extra && rl < 32 && m < g.M) ex[u] = __ldg(reinterpret_cast<const float4*>(epi_extra_ptr(g, m, n)));
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int rl = rb + 2 * u + rsub;
+                            const int rl = rb + u * rpp + rsub;
                             const long m = (long)m0 + q4 * 32 + rl;
-                            if (m >= g.M) continue;
+                            if (rl >= 32 || m >= g.M) continue;
                             float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
                             float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
                             if (g.epi == CMGAN_EPI_SWISH_DUAL) {
@@ -301,6 +313,11 @@ __global__ void __launch_bounds__(NTHREADS, ASYNC_A ? 2 : 1) gemm_rows_tc_kernel
                     }
                 }
                 __syncwarp();
+            }
+            if (!released) {          // no slab for this warp (narrow N): still part of the release count
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + 8u * buf);
             }
         }
     }
@@ -340,12 +357,16 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     const int b_tile = cfg.BN * KC * 4;
     const int nchunks = (a->Cin / KC) * a->ntaps;
     cfg.resident = (long)nchunks * b_tile <= RESIDENT_MAX ? 1 : 0;
-    const int fixed = 1024 /*alignment*/ + STG_BYTES + 256 /*barriers*/ + (cfg.resident ? nchunks * b_tile : 0);
-    const int per_stage = A_STAGE_BYTES + (cfg.resident ? 0 : b_tile);
     cfg.tmem_cols = 64;
     while (cfg.tmem_cols < 2 * cfg.BN) cfg.tmem_cols <<= 1;
-    // two co-resident CTAs per SM (twice the loads in flight, epilogues overlap) when shared memory, TMEM and registers allow it
+    // configuration A: two co-resident CTAs per SM with 4 epilogue warps each (twice the loads in flight);
+    // configuration B: one CTA per SM with 8 epilogue warps (wide N: TMEM / shared memory allow only one CTA)
+    const int resident_bytes = cfg.resident ? nchunks * b_tile : 0;
+    const int per_stage = A_STAGE_BYTES + (cfg.resident ? 0 : b_tile);
+    int fixed = 1024 /*alignment*/ + STG_BYTES4 + 256 /*barriers*/ + resident_bytes;
     int ctas = (a->pro == CMGAN_PRO_NONE && cfg.tmem_cols <= 256 && fixed + 3 * per_stage <= SMEM_LIMIT / 2) ? 2 : 1;
+    const bool epi8 = ctas == 1;
+    if (epi8) fixed += STG_BYTES8 - STG_BYTES4;
     cfg.stages = (SMEM_LIMIT / ctas - fixed) / per_stage;
     if (cfg.stages > 6) cfg.stages = 6;
     if (cfg.stages < 2) return 1;
@@ -355,15 +376,17 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) { g_num_sms = 0; cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     }
     long total = (long)nchunks * cfg.BN * KC;
     pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
     if (cmgan_check_launch("pack_b_kernel")) return -1;
     const int grid = cfg.ntiles < ctas * g_num_sms ? cfg.ntiles : ctas * g_num_sms;
-    if (a->pro == CMGAN_PRO_NONE) gemm_rows_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(*a, a->ws, cfg);
-    else gemm_rows_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(*a, a->ws, cfg);
+    if (a->pro != CMGAN_PRO_NONE) gemm_rows_tc_kernel<false, true><<<grid, NTHREADS8, smem, st>>>(*a, a->ws, cfg);
+    else if (epi8) gemm_rows_tc_kernel<true, true><<<grid, NTHREADS8, smem, st>>>(*a, a->ws, cfg);
+    else gemm_rows_tc_kernel<true, false><<<grid, NTHREADS4, smem, st>>>(*a, a->ws, cfg);
     return cmgan_check_launch("gemm_rows_tc_kernel");
 }

@@ -39,3 +39,20 @@ def test_swish_dual_epilogue():
             err = (got - ref).abs().max().item()
             print(f"[parity] swish-dual prec={prec} {name}: max-abs {err:.3e} (range {ref.abs().max().item():.3e})")
             assert err <= tol[prec] * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,T,Fw,axis", [(2, 321, 3, 0), (2, 5, 101, 1), (1, 530, 1, 0), (1, 4, 2, 0), (1, 70, 2, 0), (3, 2, 17, 1)])
+def test_attention_fwd_tensor_core(B, T, Fw, axis):
+    g = torch.Generator().manual_seed(7)
+    M = B * T * Fw
+    qkv = torch.randn(M, 192, generator=g).to(DEV)
+    E = (torch.randn(1025, 16, generator=g) * 0.5).to(DEV)
+    ref, lse_ref = torch.empty(M, 64, device=DEV), torch.empty(M, 4, device=DEV)
+    got, lse = torch.full((M, 64), float("nan"), device=DEV), torch.full((M, 4), float("nan"), device=DEV)
+    call("cmgan_attention_fwd", qkv, E, B, T, Fw, axis, ref, lse_ref)
+    call("cmgan_attention_fwd_tf32", qkv, E, B, T, Fw, axis, got, lse)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    lerr = (lse - lse_ref).abs().max().item()
+    print(f"[parity-tf32] attention fwd axis={axis} L={T if axis == 0 else Fw}: ctx max-abs {err:.3e} (range {ref.abs().max().item():.2e}), lse {lerr:.3e}")
+    assert np.isfinite(err) and err < 1e-2 * ref.abs().max().item() and lerr < 2e-2
