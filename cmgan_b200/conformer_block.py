@@ -214,7 +214,7 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
          C=G[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.attn.fn.to_out.bias"])
     dqkv = _empty(M, 3 * C, dev=dev)
     delta = _empty(M, 4, dev=dev)
-    call("cmgan_attention_bwd", S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv,
+    call("cmgan_attention_bwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_bwd", S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv,
          G[f"{p}.attn.fn.rel_pos_emb.weight"])
     dln2 = _empty(M, C, dev=dev)
     gemm(A=dqkv, lda=3 * C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=C)

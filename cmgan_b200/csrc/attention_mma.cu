@@ -187,6 +187,388 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
     }
 }
 
+
+// ============================================================================================ backward
+// Both backward kernels recompute the logits tile by tile exactly as the forward does (tf32 operands, fp32 accumulate) and use
+//   p = exp2(s - lse),  dp = dO V^T,  ds = p (dp - delta),  delta_i = dO_i . O_i
+// (ds is the gradient wrt the natural-log logits; q is held pre-scaled by 0.25 log2(e), so sums against q take a final ln 2).
+constexpr float LN2 = 0.6931471805599453f;
+
+// ---- dq, delta and dE.  A block owns one 64-query tile position and walks over many (sequence, head) items, so the relative
+// distances it touches are the same for every item and dE can be accumulated in shared memory, flushed once at the end.
+//   dQ  = dS K  +  dR E_win                 dR[i, c] = dS[i, j],  c = i_l - j_l + 63  (dS scattered skewed into the block's R buffer,
+//                                           64 queries x 127 distances; a warp writes only its own 16 rows)
+//   dEw = dR^T Q                            128 x 16 per block and key tile; each warp owns 32 distances -> plain adds into the
+//                                           block accumulator (no atomics: shared fp32 atomics are CAS loops)
+// dynamic smem: Ks | Vs | Es | Rb[64 x LDRB] | Qs[64 x 20] | dEs[(Lpad + 64) x 16]
+constexpr int LDRB = 136;
+__global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
+                                                              const float* __restrict__ ctx, const float* __restrict__ dctx,
+                                                              const float* __restrict__ lse, int n_items, int Lpad,
+                                                              float* __restrict__ delta, float* __restrict__ dqkv,
+                                                              float* __restrict__ dE) {
+    extern __shared__ __align__(16) float smem_dq[];
+    float* Ks = smem_dq;
+    float* Vs = Ks + KT * LDS_;
+    float* Es = Vs + KT * LDS_;
+    float* Rb = Es + (EW + 4) * LDS_;
+    float* Qs = Rb + QB * LDRB;
+    float* dEs = Qs + QB * LDS_;
+    const int i0 = blockIdx.y * QB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
+    const int iw = i0 + warp * 16;
+    const bool warp_active = iw < g.L;
+    const int acc_rows = Lpad + 64;
+    const int r_acc0 = i0 - Lpad + 1;                 // relative distance of accumulator row 0
+    for (int idx = tid; idx < acc_rows * D; idx += 128) dEs[idx] = 0.f;
+    for (int idx = tid; idx < QB * LDRB; idx += 128) Rb[idx] = 0.f;
+    float* R = Rb + warp * 16 * LDRB + warp * 16;     // this warp's rows; its 80-distance window starts at block column 16 warp
+    float* Qw = Qs + warp * 16 * LDS_;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int s = item / H, h = item % H;
+        const long base = seq_base(g, s);
+        // ---- per-item row operands: q (scaled), dO as A fragments; delta, lse for rows gq, gq+8
+        float qa[2][4], da[2][4], dl[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int row = iw + gq + (r & 1) * 8, col = t + (r >> 1) * 4 + ks * 8;
+                float qv = 0.f, dv = 0.f, ov = 0.f;
+                if (row < g.L) {
+                    const long rr = base + (long)row * g.tok_stride;
+                    qv = __ldg(qkv + rr * LDQ + h * D + col) * SCALE_LOG2E;
+                    dv = __ldg(dctx + rr * CQ + h * D + col);
+                    ov = __ldg(ctx + rr * CQ + h * D + col);
+                }
+                qa[ks][r] = tf32r(qv);
+                da[ks][r] = tf32r(dv);
+                dl[r & 1] = fmaf(dv, ov, dl[r & 1]);
+            }
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            dl[hrow] += __shfl_xor_sync(0xffffffffu, dl[hrow], 1);
+            dl[hrow] += __shfl_xor_sync(0xffffffffu, dl[hrow], 2);
+            const int row = iw + gq + hrow * 8;
+            if (row < g.L) {
+                const long rr = base + (long)row * g.tok_stride;
+                ls[hrow] = __ldg(lse + rr * H + h);
+                if (t == 0) delta[rr * H + h] = dl[hrow];
+            }
+        }
+        float dq[2][4];
+#pragma unroll
+        for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dq[nd][r] = 0.f;
+
+        for (int j0 = 0; j0 < g.L; j0 += KT) {
+            const int nk = min(KT, g.L - j0);
+            __syncthreads();               // previous tile's dE pass (reads Rb, Qs of every warp) is complete
+            if (j0 == 0) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) Qw[(gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8] = qa[ks][r];
+            }
+            for (int idx = tid; idx < KT * 4; idx += 128) {
+                const int r = idx >> 2, q4 = idx & 3;
+                float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+                if (r < nk) {
+                    const float* p = qkv + (base + (long)(j0 + r) * g.tok_stride) * LDQ + h * D;
+                    kv = __ldg(reinterpret_cast<const float4*>(p + CQ) + q4);
+                    vv = __ldg(reinterpret_cast<const float4*>(p + 2 * CQ) + q4);
+                }
+                *reinterpret_cast<float4*>(Ks + r * LDS_ + q4 * 4) = make_float4(tf32r(kv.x), tf32r(kv.y), tf32r(kv.z), tf32r(kv.w));
+                *reinterpret_cast<float4*>(Vs + r * LDS_ + q4 * 4) = make_float4(tf32r(vv.x), tf32r(vv.y), tf32r(vv.z), tf32r(vv.w));
+            }
+            const int rfirst = i0 - j0 - (KT - 1);
+            for (int idx = tid; idx < (EW + 4) * 4; idx += 128) {
+                const int w = idx >> 2, q4 = idx & 3;
+                const int e = clampi(rfirst + w, -MAXPOS, MAXPOS) + MAXPOS;
+                const float4 ev = __ldg(reinterpret_cast<const float4*>(E + e * D) + q4);
+                *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
+            }
+            __syncthreads();
+            if (warp_active) {
+                // ---- S = Q K^T, dP = dO V^T
+                float sc[8][4], dp[8][4];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+                    dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const float* kp = Ks + (nt * 8 + gq) * LDS_ + t + ks * 8;
+                        const float* vp = Vs + (nt * 8 + gq) * LDS_ + t + ks * 8;
+                        mma_tf32(sc[nt], qa[ks], kp[0], kp[4]);
+                        mma_tf32(dp[nt], da[ks], vp[0], vp[4]);
+                    }
+                }
+                // ---- R = Q E_win^T -> smem (this warp's rows, window columns 0..79)
+#pragma unroll
+                for (int nt = 0; nt < RW / 8; ++nt) {
+                    float rc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const float* ep = Es + (warp * 16 + nt * 8 + gq) * LDS_ + t + ks * 8;
+                        mma_tf32(rc, qa[ks], ep[0], ep[4]);
+                    }
+                    *reinterpret_cast<float2*>(R + gq * LDRB + nt * 8 + 2 * t) = make_float2(rc[0], rc[1]);
+                    *reinterpret_cast<float2*>(R + (gq + 8) * LDRB + nt * 8 + 2 * t) = make_float2(rc[2], rc[3]);
+                }
+                __syncwarp();
+                // ---- ds = exp2(s + R_skew - lse) (dp - delta), tf32
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int qrow = gq + (r >> 1) * 8, kcol = nt * 8 + 2 * t + (r & 1);
+                        const float a = sc[nt][r] + R[qrow * LDRB + qrow - kcol + (KT - 1)];
+                        float ds = exp2f(a - ls[r >> 1]) * (dp[nt][r] - dl[r >> 1]);
+                        if (kcol >= nk) ds = 0.f;
+                        sc[nt][r] = tf32r(ds);
+                    }
+                __syncwarp();
+                // ---- dR: scatter ds skewed into the same rows; the 16 window columns per row outside the band are zeroed
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = lane + 32 * u, row = idx >> 4, c = (row + 64 + (idx & 15)) % RW;
+                    R[row * LDRB + c] = 0.f;
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int qrow = gq + (r >> 1) * 8, kcol = nt * 8 + 2 * t + (r & 1);
+                        R[qrow * LDRB + qrow - kcol + (KT - 1)] = sc[nt][r];
+                    }
+                __syncwarp();
+                // ---- dQ += dS K   (A = dS re-used from the accumulator layout; keys of a k-step permuted, see forward)
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const float pa[4] = {sc[kk][0], sc[kk][2], sc[kk][1], sc[kk][3]};
+#pragma unroll
+                    for (int nd = 0; nd < 2; ++nd) {
+                        const float* kp = Ks + (kk * 8 + 2 * t) * LDS_ + nd * 8 + gq;
+                        mma_tf32(dq[nd], pa, kp[0], kp[LDS_]);
+                    }
+                }
+                // ---- dQ += dR E_win  (K = 80 distances)
+#pragma unroll
+                for (int kk = 0; kk < RW / 8; ++kk) {
+                    const float ra[4] = {R[gq * LDRB + kk * 8 + t], R[(gq + 8) * LDRB + kk * 8 + t], R[gq * LDRB + kk * 8 + t + 4],
+                                         R[(gq + 8) * LDRB + kk * 8 + t + 4]};
+#pragma unroll
+                    for (int nd = 0; nd < 2; ++nd) {
+                        const float* ep = Es + (warp * 16 + kk * 8 + t) * LDS_ + nd * 8 + gq;
+                        mma_tf32(dq[nd], ra, ep[0], ep[4 * LDS_]);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- dE_win = dR^T Q over the block: M = 128 distances (32 per warp), K = 64 queries, N = 16
+            {
+                const int arow0 = (i0 - j0 - (KT - 1)) - r_acc0 + warp * 32;      // accumulator row of this warp's first distance
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    float ec[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                    for (int ks = 0; ks < QB / 8; ++ks) {
+                        const float* rp = Rb + (t + 8 * ks) * LDRB + warp * 32 + 16 * mt + gq;
+                        const float ta[4] = {rp[0], rp[8], rp[4 * LDRB], rp[4 * LDRB + 8]};
+#pragma unroll
+                        for (int nd = 0; nd < 2; ++nd) {
+                            const float* qp = Qs + (t + 8 * ks) * LDS_ + nd * 8 + gq;
+                            mma_tf32(ec[nd], ta, qp[0], qp[4 * LDS_]);
+                        }
+                    }
+#pragma unroll
+                    for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            float2* ap = reinterpret_cast<float2*>(dEs + (arow0 + 16 * mt + gq + hrow * 8) * D + nd * 8 + 2 * t);
+                            float2 v = *ap;
+                            v.x += ec[nd][hrow * 2]; v.y += ec[nd][hrow * 2 + 1];
+                            *ap = v;
+                        }
+                }
+            }
+        }
+        if (warp_active) {
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int i = iw + gq + hrow * 8;
+                if (i >= g.L) continue;
+                const long row = base + (long)i * g.tok_stride;
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd)
+                    *reinterpret_cast<float2*>(dqkv + row * LDQ + h * D + nd * 8 + 2 * t) =
+                        make_float2(0.25f * dq[nd][hrow * 2], 0.25f * dq[nd][hrow * 2 + 1]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < acc_rows * D; idx += 128) {
+        const int rr = r_acc0 + idx / D;
+        if (rr < -(g.L - 1) || rr > g.L - 1) continue;
+        const float v = dEs[idx];
+        if (v != 0.f) atomicAdd(dE + (clampi(rr, -MAXPOS, MAXPOS) + MAXPOS) * D + (idx % D), v * LN2);
+    }
+}
+
+// ---- dk, dv.  One warp owns 16 keys; queries are visited in tiles of 64.  Everything is held transposed (rows = keys):
+//   S^T = K Q^T + skew(R2),  R2 = Q_tile E_win^T (64 x 127, computed once per tile by the whole block)
+//   dV += P^T dO,  dK += dS^T Q
+constexpr int LDR2 = 132;
+__global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
+                                                               const float* __restrict__ dctx, const float* __restrict__ lse,
+                                                               const float* __restrict__ delta, float* __restrict__ dqkv) {
+    extern __shared__ __align__(16) float smem_kv[];
+    float* Qs = smem_kv;
+    float* Os = Qs + QB * LDS_;
+    float* Es = Os + QB * LDS_;
+    float* R2 = Es + (EW + 4) * LDS_;
+    float* Ls = R2 + QB * LDR2;
+    float* Dl = Ls + QB;
+    const int s = blockIdx.x / H, h = blockIdx.x % H;
+    const int j0 = blockIdx.y * KT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
+    const long base = seq_base(g, s);
+    const int jw = j0 + warp * 16;
+    const bool warp_active = jw < g.L;
+
+    float ka[2][4], va[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = jw + gq + (r & 1) * 8, col = t + (r >> 1) * 4 + ks * 8;
+            float kv = 0.f, vv = 0.f;
+            if (row < g.L) {
+                const float* p = qkv + (base + (long)row * g.tok_stride) * LDQ + h * D + col;
+                kv = __ldg(p + CQ);
+                vv = __ldg(p + 2 * CQ);
+            }
+            ka[ks][r] = tf32r(kv);
+            va[ks][r] = tf32r(vv);
+        }
+    float dk[2][4], dv[2][4];
+#pragma unroll
+    for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { dk[nd][r] = 0.f; dv[nd][r] = 0.f; }
+
+    for (int i0 = 0; i0 < g.L; i0 += QB) {
+        const int nq = min(QB, g.L - i0);
+        __syncthreads();
+        for (int idx = tid; idx < QB * 4; idx += 128) {
+            const int r = idx >> 2, q4 = idx & 3;
+            float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), ov = qv;
+            if (r < nq) {
+                const long rr = base + (long)(i0 + r) * g.tok_stride;
+                qv = __ldg(reinterpret_cast<const float4*>(qkv + rr * LDQ + h * D) + q4);
+                ov = __ldg(reinterpret_cast<const float4*>(dctx + rr * CQ + h * D) + q4);
+            }
+            *reinterpret_cast<float4*>(Qs + r * LDS_ + q4 * 4) = make_float4(tf32r(qv.x * SCALE_LOG2E), tf32r(qv.y * SCALE_LOG2E),
+                                                                             tf32r(qv.z * SCALE_LOG2E), tf32r(qv.w * SCALE_LOG2E));
+            *reinterpret_cast<float4*>(Os + r * LDS_ + q4 * 4) = make_float4(tf32r(ov.x), tf32r(ov.y), tf32r(ov.z), tf32r(ov.w));
+        }
+        for (int r = tid; r < QB; r += 128) {
+            float l = INFINITY, d = 0.f;                        // queries past the end: p = exp2(-inf) = 0
+            if (r < nq) {
+                const long rr = base + (long)(i0 + r) * g.tok_stride;
+                l = __ldg(lse + rr * H + h);
+                d = __ldg(delta + rr * H + h);
+            }
+            Ls[r] = l; Dl[r] = d;
+        }
+        const int rfirst = i0 - j0 - (KT - 1);                  // window column c <-> distance rfirst + c,  c = il - jl + 63
+        for (int idx = tid; idx < (EW + 4) * 4; idx += 128) {
+            const int w = idx >> 2, q4 = idx & 3;
+            const int e = clampi(rfirst + w, -MAXPOS, MAXPOS) + MAXPOS;
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(E + e * D) + q4);
+            *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
+        }
+        __syncthreads();
+        // ---- R2 rows 16 warp .. 16 warp + 15 (queries), all 128 window columns
+        {
+            float qa[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) qa[ks][r] = Qs[(warp * 16 + gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8];
+#pragma unroll 4
+            for (int nt = 0; nt < 16; ++nt) {
+                float rc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const float* ep = Es + (nt * 8 + gq) * LDS_ + t + ks * 8;
+                    mma_tf32(rc, qa[ks], ep[0], ep[4]);
+                }
+                *reinterpret_cast<float2*>(R2 + (warp * 16 + gq) * LDR2 + nt * 8 + 2 * t) = make_float2(rc[0], rc[1]);
+                *reinterpret_cast<float2*>(R2 + (warp * 16 + gq + 8) * LDR2 + nt * 8 + 2 * t) = make_float2(rc[2], rc[3]);
+            }
+        }
+        __syncthreads();
+        if (!warp_active) continue;
+
+        // ---- S^T = K Q^T, dP^T = V dO^T     (rows = keys gq, gq+8 of this warp; columns = queries of the tile)
+        float sc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const float* qp = Qs + (nt * 8 + gq) * LDS_ + t + ks * 8;
+                const float* op = Os + (nt * 8 + gq) * LDS_ + t + ks * 8;
+                mma_tf32(sc[nt], ka[ks], qp[0], qp[4]);
+                mma_tf32(dp[nt], va[ks], op[0], op[4]);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float2 l2 = *reinterpret_cast<const float2*>(Ls + nt * 8 + 2 * t);
+            const float2 d2 = *reinterpret_cast<const float2*>(Dl + nt * 8 + 2 * t);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int jl = warp * 16 + gq + (r >> 1) * 8, il = nt * 8 + 2 * t + (r & 1);
+                const float a = sc[nt][r] + R2[il * LDR2 + il - jl + (KT - 1)];
+                const float p = exp2f(a - ((r & 1) ? l2.y : l2.x));
+                sc[nt][r] = tf32r(p);
+                dp[nt][r] = tf32r(p * (dp[nt][r] - ((r & 1) ? d2.y : d2.x)));
+            }
+        }
+        // ---- dV += P^T dO,  dK += dS^T Q   (A from the accumulator layout; queries of a k-step permuted)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float pa[4] = {sc[kk][0], sc[kk][2], sc[kk][1], sc[kk][3]};
+            const float sa[4] = {dp[kk][0], dp[kk][2], dp[kk][1], dp[kk][3]};
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd) {
+                const float* op = Os + (kk * 8 + 2 * t) * LDS_ + nd * 8 + gq;
+                const float* qp = Qs + (kk * 8 + 2 * t) * LDS_ + nd * 8 + gq;
+                mma_tf32(dv[nd], pa, op[0], op[LDS_]);
+                mma_tf32(dk[nd], sa, qp[0], qp[LDS_]);
+            }
+        }
+    }
+    if (!warp_active) return;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+        const int j = jw + gq + hrow * 8;
+        if (j >= g.L) continue;
+        float* p = dqkv + (base + (long)j * g.tok_stride) * LDQ + h * D + 2 * t;
+#pragma unroll
+        for (int nd = 0; nd < 2; ++nd) {
+            *reinterpret_cast<float2*>(p + CQ + nd * 8) = make_float2(LN2 * dk[nd][hrow * 2], LN2 * dk[nd][hrow * 2 + 1]);
+            *reinterpret_cast<float2*>(p + 2 * CQ + nd * 8) = make_float2(dv[nd][hrow * 2], dv[nd][hrow * 2 + 1]);
+        }
+    }
+}
+
 }  // namespace
 
 // tf32 tensor-core forward (same outputs as cmgan_attention_fwd; logits carry tf32 operand rounding)
@@ -198,4 +580,38 @@ CMGAN_API int cmgan_attention_fwd_tf32(const float* qkv, const float* E, int B, 
     dim3 grid(g.n_seq * H, cdiv(g.L, QB));
     attn_fwd_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, g, E, ctx, lse);
     return cmgan_check_launch("attn_fwd_mma_kernel");
+}
+
+// tf32 tensor-core backward (same contract as cmgan_attention_bwd: dqkv overwritten, dE accumulated, delta scratch)
+CMGAN_API int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
+                                       int T, int F, int axis, float* delta, float* dqkv, float* dE, void* stream) {
+    CMGAN_REQUIRE(qkv && E && ctx && dctx && lse && delta && dqkv && dE, "cmgan_attention_bwd_tf32: null pointer");
+    CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_attention_bwd_tf32: axis must be 0 (time) or 1 (freq)");
+    SeqGeom g = make_seq_geom(B, T, F, axis);
+    if (g.n_seq == 0 || g.L == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ntile = cdiv(g.L, QB), Lpad = ntile * KT;
+    const int smem_dq = (2 * KT * LDS_ + (EW + 4) * LDS_ + QB * LDRB + QB * LDS_ + (Lpad + 64) * D) * (int)sizeof(float);
+    const int smem_kv = (2 * QB * LDS_ + (EW + 4) * LDS_ + QB * LDR2 + 2 * QB) * (int)sizeof(float);
+    CMGAN_REQUIRE(smem_dq <= 227 * 1024, "cmgan_attention_bwd_tf32: sequence length %d too long for the shared dE accumulator", g.L);
+    static int smem_dq_set = 0;
+    static bool kv_set = false;
+    if (smem_dq > smem_dq_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
+        CMGAN_REQUIRE(e == cudaSuccess, "cmgan_attention_bwd_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        smem_dq_set = smem_dq;
+    }
+    if (!kv_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
+        CMGAN_REQUIRE(e == cudaSuccess, "cmgan_attention_bwd_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        kv_set = true;
+    }
+    const int n_items = g.n_seq * H;
+    int ng = (148 * 2) / ntile;                      // one wave of 2 resident blocks per SM
+    if (ng < 1) ng = 1;
+    if (ng > n_items) ng = n_items;
+    attn_bwd_dq_mma_kernel<<<dim3(ng, ntile), 128, smem_dq, st>>>(qkv, g, E, ctx, dctx, lse, n_items, Lpad, delta, dqkv, dE);
+    if (cmgan_check_launch("attn_bwd_dq_mma_kernel")) return -1;
+    attn_bwd_dkv_mma_kernel<<<dim3(n_items, ntile), 128, smem_kv, st>>>(qkv, g, E, dctx, lse, delta, dqkv);
+    return cmgan_check_launch("attn_bwd_dkv_mma_kernel");
 }

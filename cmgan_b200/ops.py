@@ -14,7 +14,7 @@ import torch
 from ._lib import GemmArgs, MAX_TAPS, lib
 
 # number of kernels each entry point launches (for bench.py's ``gpu_launches``)
-_KERNELS = {"cmgan_attention_bwd": 3}
+_KERNELS = {"cmgan_attention_bwd": 3, "cmgan_attention_bwd_tf32": 2}
 LAUNCHES = 0
 PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" else 0   # default for every dense contraction
 SEED_DEV = None  # optional uint64 device counter added to every dropout seed (set by the trainer for CUDA-graph replay)

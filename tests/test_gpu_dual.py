@@ -56,3 +56,32 @@ def test_attention_fwd_tensor_core(B, T, Fw, axis):
     lerr = (lse - lse_ref).abs().max().item()
     print(f"[parity-tf32] attention fwd axis={axis} L={T if axis == 0 else Fw}: ctx max-abs {err:.3e} (range {ref.abs().max().item():.2e}), lse {lerr:.3e}")
     assert np.isfinite(err) and err < 1e-2 * ref.abs().max().item() and lerr < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,Fw,axis", [(1, 70, 3, 0), (2, 5, 101, 1), (1, 321, 2, 0), (1, 3, 130, 1), (3, 64, 5, 0), (1, 700, 1, 0)])
+def test_attention_bwd_tensor_core(B, T, Fw, axis):
+    """tf32 mma.sync backward (dq / dk / dv / dE, skewed relative-position terms) vs the exact fp32 backward"""
+    g = torch.Generator().manual_seed(11)
+    M = B * T * Fw
+    qkv = torch.randn(M, 192, generator=g).to(DEV)
+    E = (torch.randn(1025, 16, generator=g) * 0.5).to(DEV)
+    dctx = torch.randn(M, 64, generator=g).to(DEV)
+    ctx, lse = torch.empty(M, 64, device=DEV), torch.empty(M, 4, device=DEV)
+    call("cmgan_attention_fwd", qkv, E, B, T, Fw, axis, ctx, lse)
+    out = {}
+    for name in ("cmgan_attention_bwd", "cmgan_attention_bwd_tf32"):
+        delta = torch.full((M, 4), float("nan"), device=DEV)
+        dqkv = torch.full((M, 192), float("nan"), device=DEV)
+        dE = torch.zeros(1025, 16, device=DEV)
+        call(name, qkv, E, ctx, dctx, lse, B, T, Fw, axis, delta, dqkv, dE)
+        torch.cuda.synchronize()
+        out[name] = (dqkv, dE, delta)
+    (r_dqkv, r_dE, r_dl), (g_dqkv, g_dE, g_dl) = out["cmgan_attention_bwd"], out["cmgan_attention_bwd_tf32"]
+    L = T if axis == 0 else Fw
+    for nm, got, ref in (("dq", g_dqkv[:, :64], r_dqkv[:, :64]), ("dk", g_dqkv[:, 64:128], r_dqkv[:, 64:128]),
+                         ("dv", g_dqkv[:, 128:], r_dqkv[:, 128:]), ("dE", g_dE, r_dE), ("delta", g_dl, r_dl)):
+        err = (got - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print(f"[parity-tf32] attention bwd axis={axis} L={L} {nm}: max-abs {err:.3e} (range {scale:.2e})")
+        assert np.isfinite(err) and err < 1e-2 * scale, nm
