@@ -58,7 +58,7 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
 
 struct TcCfg { int BN, stages, tmem_cols, resident, ntiles; };
 
-template <bool ASYNC_A, bool EPI8>
+template <bool ASYNC_A, bool EPI8, int EPI>
 __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI8) ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
                                                                     const TcCfg cfg) {
     extern __shared__ uint8_t smem_raw[];
@@ -241,76 +241,133 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
         __syncwarp();
     } else {
         // ================================ epilogue (warps 6-9, or 6-13 with EPI8) ================================
-        // a warp may only touch its TMEM lane quarter (warp % 4); with EPI8 two warps share a quarter and split the column slabs
+        // a warp may only touch its TMEM lane quarter (warp % 4); with EPI8 two warps share a quarter and alternate 64-column slabs.
+        // Per slab: 4 x tcgen05.ld in flight -> one wait -> 16 st.shared.v4 (own row) -> the warp re-reads the slab as coalesced
+        // 256-byte row segments (16 lanes x float4, 2 rows per pass), applies the compile-time epilogue and stores.
         const int q4 = warp & 3;
         const int ew = warp - 6;
-        const int half = ew >> 2, nhalf = EPI8 ? 2 : 1;
-        const int W = EPI8 ? max(16, min(SLAB, BN / 2)) : SLAB;          // slab width (columns)
-        const int lpr = W / 4;                                           // lanes per row (float4 each)
-        const int rpp = 32 / lpr;                                        // rows per pass
+        const int half = EPI8 ? (ew >> 2) : 0;
+        constexpr int NH = EPI8 ? 2 : 1;
         float* stg = reinterpret_cast<float*>(base_ptr + (sStg - base)) + ew * 32 * STG_LD;
-        const int col4 = (lane % lpr) * 4;
-        const int rsub = lane / lpr;
-        const int nslabs = (BN + W - 1) / W;
+        const int col4 = (lane & 15) * 4;
+        const int rsub = lane >> 4;
+        const int nslabs = (BN + SLAB - 1) / SLAB;
+        constexpr bool DROPS = EPI == CMGAN_EPI_DROP_RES || EPI == CMGAN_EPI_DSWISH_DROP || EPI == CMGAN_EPI_SWISH_DUAL;
+        const uint32_t seed32 = DROPS ? cmgan_seed32(eff_seed(g)) : 0u;
+        const uint32_t thr16 = g.drop_thr >> 16;
+        const bool drop_on = DROPS && g.drop_thr != 0u;
+        const float inv_keep = g.inv_keep, alpha = g.alpha;
+        // auxiliary operand read at the output position: R (DROP_RES, optional), aux (DSWISH_DROP / DBNSWISH), old C (ACC)
+        const float* xbase = nullptr;
+        long ldx = 0;
+        if (EPI == CMGAN_EPI_DROP_RES) { xbase = g.R; ldx = g.ldr; }
+        else if (EPI == CMGAN_EPI_DSWISH_DROP || EPI == CMGAN_EPI_DBNSWISH) { xbase = g.aux; ldx = g.ldaux; }
+        else if (EPI == CMGAN_EPI_ACC) { xbase = g.C; ldx = g.ldc; }
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int buf = lt & 1;
-            const int m0 = (blockIdx.x + lt * gridDim.x) * BM;
+            const int mrow0 = (blockIdx.x + lt * gridDim.x) * BM + q4 * 32;
+            const int rows_valid = g.M - mrow0;                 // rows of this quarter inside the matrix (may be <= 0 or >= 32)
+            const int npass = rsub < rows_valid ? min(16, (rows_valid - rsub + 1) >> 1) : 0;
+            const long mfirst = (long)mrow0 + rsub;
+            const long xstep = 2 * ldx;
+            // the auxiliary operand does not depend on the accumulator: its first loads are issued before waiting for the MMAs,
+            // later batches (4 passes = 8 rows each) one batch ahead of their use
+            float4 ex[2][4];
+            auto prefetch = [&](int sl, int b4, float4* dst) {
+                const int n = sl * SLAB + col4;
+                if (xbase == nullptr || n >= BN) return;
+                const float* xp = xbase + mfirst * ldx + n + (long)(b4 * 4) * xstep;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (b4 * 4 + u < npass) dst[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
+            };
+            if (half < nslabs) prefetch(half, 0, ex[0]);
             mbar_wait(tfull_bar + 8u * buf, (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * acc_stride + ((uint32_t)(q4 * 32) << 16);
             bool released = false;
-            for (int sl = half; sl < nslabs; sl += nhalf) {
-                const int n0 = sl * W;
-                const int ncols = min(W, BN - n0);
-                for (int q = 0; q < ncols; q += 16) {
-                    float acc[16];
-                    tmem_ld16(trow + (uint32_t)(n0 + q), acc);
+            for (int sl = half; sl < nslabs; sl += NH) {
+                const int n0 = sl * SLAB;
+                const int ncols = min(SLAB, BN - n0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4*>(stg + lane * STG_LD + q + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                for (int hq = 0; hq < 2; ++hq) {              // 32 columns at a time: two tcgen05.ld in flight per wait
+                    if (hq * 32 >= ncols) break;
+                    uint32_t r[32];
+                    tmem_ld16_nowait(trow + (uint32_t)(n0 + hq * 32), r);
+                    if (hq * 32 + 16 < ncols) tmem_ld16_nowait(trow + (uint32_t)(n0 + hq * 32 + 16), r + 16);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (hq * 32 + q * 16 < ncols) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(stg + lane * STG_LD + hq * 32 + q * 16 + 4 * j) =
+                                    make_uint4(r[16 * q + 4 * j], r[16 * q + 4 * j + 1], r[16 * q + 4 * j + 2], r[16 * q + 4 * j + 3]);
+                        }
                 }
-                if (sl + nhalf >= nslabs) {                   // this warp's last slab is out of TMEM: the accumulator buffer may be overwritten
+                if (sl + NH >= nslabs) {                      // this warp's last slab is out of TMEM: the accumulator buffer may be overwritten
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar + 8u * buf);
                     released = true;
                 }
                 __syncwarp();
-                const int n = n0 + col4;
-                if (col4 < ncols) {
+                if (col4 < ncols && npass > 0) {
+                    const int n = n0 + col4;
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), e0v = bias4, e1v = bias4;
                     if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-                    if (g.epi == CMGAN_EPI_DBNSWISH) { e0v = __ldg(reinterpret_cast<const float4*>(g.e0 + n)); e1v = __ldg(reinterpret_cast<const float4*>(g.e1 + n)); }
-                    const bool extra = epi_needs_extra(g);
-                    for (int rb = 0; rb < 32; rb += 8 * rpp) {     // 8 passes per batch: issue all auxiliary loads first
-                        float4 ex[8];
+                    if (EPI == CMGAN_EPI_DBNSWISH) { e0v = __ldg(reinterpret_cast<const float4*>(g.e0 + n)); e1v = __ldg(reinterpret_cast<const float4*>(g.e1 + n)); }
+                    float* cptr = g.C ? g.C + mfirst * g.ldc + n : nullptr;
+                    float* c2ptr = EPI == CMGAN_EPI_SWISH_DUAL ? g.C2 + mfirst * g.ldc2 + n : nullptr;
+                    const float* sptr = stg + rsub * STG_LD + col4;
+                    const long cstep = 2 * (long)g.ldc, c2step = 2 * (long)g.ldc2;
+                    const uint32_t pair = (uint32_t)(((unsigned long long)mfirst * (unsigned long long)g.N + (unsigned long long)n) >> 1);
+                    const uint32_t pstep = (uint32_t)g.N;       // two rows further = N pairs further
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int rl = rb + u * rpp + rsub;
-                            const long m = (long)m0 + q4 * 32 + rl;
-                            ex[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (extra && rl < 32 && m < g.M) ex[u] = __ldg(reinterpret_cast<const float4*>(epi_extra_ptr(g, m, n)));
-                        }
+                    for (int b4 = 0; b4 < 4; ++b4) {
+                        if (b4 < 3) prefetch(sl, b4 + 1, ex[(b4 + 1) & 1]);
+                        else if (sl + NH < nslabs) prefetch(sl + NH, 0, ex[0]);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int rl = rb + u * rpp + rsub;
-                            const long m = (long)m0 + q4 * 32 + rl;
-                            if (rl >= 32 || m >= g.M) continue;
-                            float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + col4);
-                            float vv[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
-                            if (g.epi == CMGAN_EPI_SWISH_DUAL) {
-                                if (g.C) *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                                float o[4];
-                                cmgan_drop_scale4(eff_seed(g), (uint64_t)m * g.N + n, g.drop_thr, g.inv_keep, o);
+                        for (int u = 0; u < 4; ++u) {
+                            const int ps = b4 * 4 + u;
+                            if (ps >= npass) break;
+                            const float4 a = *reinterpret_cast<const float4*>(sptr + ps * 2 * STG_LD);
+                            float v[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
+                            float ds[4] = {1.f, 1.f, 1.f, 1.f};
+                            if (DROPS && drop_on) {
+                                const uint32_t pr = pair + (uint32_t)ps * pstep;
+                                const uint32_t h0 = cmgan_mix32((pr * 0x9E3779B1u) ^ seed32), h1 = cmgan_mix32(((pr + 1u) * 0x9E3779B1u) ^ seed32);
+                                ds[0] = (h0 & 0xFFFFu) >= thr16 ? inv_keep : 0.f; ds[1] = (h0 >> 16) >= thr16 ? inv_keep : 0.f;
+                                ds[2] = (h1 & 0xFFFFu) >= thr16 ? inv_keep : 0.f; ds[3] = (h1 >> 16) >= thr16 ? inv_keep : 0.f;
+                            }
+                            const float4 xe = ex[b4 & 1][u];
+                            const float x[4] = {xe.x, xe.y, xe.z, xe.w};
+                            if (EPI == CMGAN_EPI_SWISH_DUAL) {
+                                if (cptr) *reinterpret_cast<float4*>(cptr + ps * cstep) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) o[j] *= swishf_(vv[j]);
-                                *reinterpret_cast<float4*>(g.C2 + m * g.ldc2 + n) = make_float4(o[0], o[1], o[2], o[3]);
+                                for (int j = 0; j < 4; ++j) v[j] = swishf_(v[j]) * ds[j];
+                                *reinterpret_cast<float4*>(c2ptr + ps * c2step) = make_float4(v[0], v[1], v[2], v[3]);
                                 continue;
                             }
-                            epilogue4(g, vv, m, n, ex[u], e0v, e1v);
-                            *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            if (EPI == CMGAN_EPI_DROP_RES) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] = alpha * v[j] * ds[j] + (xbase ? x[j] : 0.f);
+                            } else if (EPI == CMGAN_EPI_DSWISH_DROP) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(x[j]) * ds[j];
+                            } else if (EPI == CMGAN_EPI_DBNSWISH) {
+                                const float sa[4] = {e0v.x, e0v.y, e0v.z, e0v.w}, sb[4] = {e1v.x, e1v.y, e1v.z, e1v.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(fmaf(x[j], sa[j], sb[j]));
+                            } else if (EPI == CMGAN_EPI_ACC) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] = alpha * v[j] + x[j];
+                            }
+                            *reinterpret_cast<float4*>(cptr + ps * cstep) = make_float4(v[0], v[1], v[2], v[3]);
                         }
                     }
+                } else if (sl + NH < nslabs) {
+                    prefetch(sl + NH, 0, ex[0]);
                 }
                 __syncwarp();
             }
@@ -347,6 +404,18 @@ int tc_supported(const CmganGemmArgs* a) {
 
 int g_num_sms = 0;
 
+template <bool ASYNC_A, bool EPI8, int EPI>
+int launch_variant(const CmganGemmArgs& a, const TcCfg& cfg, int grid, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) { cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+        attr_set = true;
+    }
+    gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI><<<grid, EPI8 ? NTHREADS8 : NTHREADS4, smem, st>>>(a, a.ws, cfg);
+    return 0;
+}
+
 }  // namespace
 
 // tf32 tensor-core path of cmgan_gemm_rows (same contract).  Returns 1 if the shape is not covered (caller falls back).
@@ -376,17 +445,30 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_rows_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) { g_num_sms = 0; cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     }
     long total = (long)nchunks * cfg.BN * KC;
     pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
     if (cmgan_check_launch("pack_b_kernel")) return -1;
     const int grid = cfg.ntiles < ctas * g_num_sms ? cfg.ntiles : ctas * g_num_sms;
-    if (a->pro != CMGAN_PRO_NONE) gemm_rows_tc_kernel<false, true><<<grid, NTHREADS8, smem, st>>>(*a, a->ws, cfg);
-    else if (epi8) gemm_rows_tc_kernel<true, true><<<grid, NTHREADS8, smem, st>>>(*a, a->ws, cfg);
-    else gemm_rows_tc_kernel<true, false><<<grid, NTHREADS4, smem, st>>>(*a, a->ws, cfg);
+    const int variant = a->pro != CMGAN_PRO_NONE ? 0 : (epi8 ? 1 : 2);
+    int rc = -2;
+#define CMGAN_TC_LAUNCH(E)                                                                                            \
+    case E:                                                                                                           \
+        rc = variant == 0   ? launch_variant<false, true, E>(*a, cfg, grid, smem, st)                                 \
+             : variant == 1 ? launch_variant<true, true, E>(*a, cfg, grid, smem, st)                                  \
+                            : launch_variant<true, false, E>(*a, cfg, grid, smem, st);                                \
+        break;
+    switch (a->epi) {
+        CMGAN_TC_LAUNCH(CMGAN_EPI_NONE)
+        CMGAN_TC_LAUNCH(CMGAN_EPI_DROP_RES)
+        CMGAN_TC_LAUNCH(CMGAN_EPI_DSWISH_DROP)
+        CMGAN_TC_LAUNCH(CMGAN_EPI_DBNSWISH)
+        CMGAN_TC_LAUNCH(CMGAN_EPI_ACC)
+        CMGAN_TC_LAUNCH(CMGAN_EPI_SWISH_DUAL)
+        default: break;
+    }
+#undef CMGAN_TC_LAUNCH
+    if (rc == -2) { cmgan_set_error("gemm_rows_tc: unknown epilogue %d", a->epi); return -1; }
+    if (rc) return -1;
     return cmgan_check_launch("gemm_rows_tc_kernel");
 }

@@ -1,12 +1,15 @@
 // tf32 tensor-core weight gradient:  dW(tap, k, n) += sum_m pro(A[in_row(m, tap), k]) * prod(D[m, n])   (gemm_args.h, wgrad form)
 //
 // The reduction runs over the rows m, so both MMA operands are "MN-major": a stage holds 32 rows of A (32 x 128 k) and of D
-// (32 x N) exactly as they lie in memory (rows of 128 B pieces), in the canonical MN-major SWIZZLE_128B layout
-//   atom(kb, blk) = 8 rows x 128 B at  blk * LBO + kb * 1024,   16-byte chunk j of row r stored at chunk j ^ r,
-// and tcgen05.mma (kind::tf32, M = 128 = k tile, N, K = 8 rows) accumulates the (128 x N) tile of dW in TMEM over a chunk of
+// (32 x N) exactly as they lie in memory (rows of 128 B pieces), in the MN-major SWIZZLE_128B_BASE32B layout tf32 requires
+// (descriptor layout type 1): 32-wide M/N blocks 4096 B apart (LBO), 8-row K groups 1024 B apart, 4-row sub-groups 512 B apart
+// (SBO), a row = 128 B whose 32-byte granule q is stored at granule q ^ (row & 3);
+// tcgen05.mma (kind::tf32, M = 128 = k tile, N, K = 8 rows) accumulates the (128 x N) tile of dW in TMEM over a chunk of
 // rows; the epilogue adds the tile into dW with red.global (the parameter-gradient buffer is zeroed once per step).
 // Grid: (row chunks) x (taps * k tiles).  Warps 0-3 load (cp.async when the operand needs no transform, else registers with the
-// same prologues as the forward GEMM / the dropout scale on D) and later run the epilogue; warp 4 issues the MMAs.
+// same prologues as the forward GEMM / the dropout scale on D) and later run the epilogue; warp 8 issues the MMAs.
+// Bias gradient for free: when Cin is not a multiple of 128 the k tile has spare (zero) rows; the row k = Cin is filled with ones
+// instead, so that accumulator row holds sum_m D[m, n] = dbias (otherwise colsum_kernel computes it in a second pass).
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_device.cuh"
@@ -22,6 +25,7 @@ constexpr int A_STAGE = RS * MO * 4; // 16 KB
 constexpr int NPROD = 256;            // 8 loader warps (warps 0-3 also run the epilogue)
 constexpr int NTHREADS = 288;
 constexpr uint32_t BLK = 4096;       // bytes between 32-wide M/N blocks (4 row groups x 1024)
+__device__ float4 g_ones4 = {1.f, 1.f, 1.f, 1.f};
 
 __device__ __forceinline__ void advance_row(const CmganGemmArgs& g, RowInfo& r, int by) {
     r.x += by;
@@ -69,6 +73,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
         const int aj = tid & 7, ami = (tid >> 3) & 3, arg = tid >> 5;
         const int ak = k0 + ami * 32 + aj * 4;
         const bool ak_ok = ak < g.Cin;
+        const bool ones_col = g.dbias != nullptr && tap == 0 && ak == g.Cin;      // this thread's chunk starts at the spare row k = Cin
         uint32_t a_off[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a_off[i] = ami * BLK + (arg * 4 + i) * 128 + ((((aj >> 1) ^ i) << 5) | ((aj & 1) << 4));
@@ -139,8 +144,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                 for (int i = 0; i < 4; ++i) {
                     if (A_ASYNC) {
                         const bool ok = arow[i] >= 0 && ak_ok;
-                        cp_async16(abase + a_off[i], g.A + (ok ? g.tap_off[tap] + arow[i] * g.lda + ak : 0), ok ? 16u : 0u);
+                        const float* src = ones_col ? reinterpret_cast<const float*>(&g_ones4) : g.A + (ok ? g.tap_off[tap] + arow[i] * g.lda + ak : 0);
+                        cp_async16(abase + a_off[i], src, (ok || ones_col) ? 16u : 0u);
                     } else {
+                        if (ones_col) av[i] = make_float4(1.f, 1.f, 1.f, 1.f);
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(abase + a_off[i]), "f"(to_tf32(av[i].x)), "f"(to_tf32(av[i].y)),
                                      "f"(to_tf32(av[i].z)), "f"(to_tf32(av[i].w)) : "memory");
                     }
@@ -178,10 +185,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int k = k0 + warp * 32 + lane;
+        const bool bias_row = g.dbias != nullptr && tap == 0 && k == g.Cin;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int n0 = 0; n0 < NB; n0 += 16) {
             float acc[16];
             tmem_ld16(trow + (uint32_t)n0, acc);
+            if (bias_row) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
+            }
             if (k < g.Cin) {
                 float* dst = g.C + (long)tap * g.sb_tap + (long)k * g.sb_k;
 #pragma unroll
@@ -296,7 +309,7 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     else if (da) rc = launch<false, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     else rc = launch<false, false>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     if (rc) return rc;
-    if (a->dbias) {
+    if (a->dbias && a->Cin % MO == 0) {       // no spare accumulator row for the fused column sum
         const int rpb = 64 * (256 / a->N > 0 ? 256 / a->N : 1);     // ~64 rows per thread -> thousands of blocks
         colsum_kernel<<<cdiv(a->M, rpb), 256, 0, st>>>(a->D, a->ldd, a->M, a->N, a->prod, a->alpha, a->seed, a->drop_thr, a->inv_keep, rpb, a->dbias, a->seed_dev);
         return cmgan_check_launch("colsum_kernel");
