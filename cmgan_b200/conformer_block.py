@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
-from .ops import EPI_ACC, EPI_DBNSWISH, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_SWISH_DUAL, PRO_DROP, call, gemm
+from .ops import EPI_ACC, EPI_DBNSWISH, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_SWISH_DUAL, call, gemm
 
 C = 64          # num_channel (the kernels are specialised for 64 channels = 4 heads x 16)
 CAT = 5 * C     # width of a dense-block concat buffer: [out4 | out3 | out2 | out1 | x]
@@ -161,28 +161,37 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     M = dy.shape[0]
     p, axis, dp, da, sd = S["p"], S["axis"], S["dp"], S["da"], S["sd"]
 
-    def ff_bwd(dout, xin, f, name, s1, s2, res2=None):
-        # out = xin + 0.5 * drop2(W2 a + b2),  a = swish(h) * drop1,  h = W1 LN(xin) + b1
+    def ln_bwd(dyv, xv, st, name, res, res2, zalpha=None, zseed=0, zp=0.0):
+        """LayerNorm backward (+ residual gradients); with ``zalpha`` also the dropout-scaled copy that enters the next residual
+        branch (dz = zalpha * mask(zseed) * dx), so that branch's GEMMs read a plain operand"""
+        dxv = _empty(M, C, dev=dev)
+        args = (dyv, C, xv, C, st, P[f"{name}.weight"], M, res, C if res is not None else 0, res2, C if res2 is not None else 0, dxv, C,
+                G[f"{name}.weight"], G[f"{name}.bias"])
+        if zalpha is None:
+            call("cmgan_ln_bwd", *args)
+            return dxv, None
+        dzv = _empty(M, C, dev=dev)
+        thr, inv = ops.drop_params(zp)
+        call("cmgan_ln_bwd_drop", *args, dzv, C, float(zalpha), zseed & 0xFFFFFFFFFFFFFFFF, thr, inv, ops.SEED_DEV)
+        return dxv, dzv
+
+    def ff_bwd(dout, dz, xin, f, name, s1, res2=None, **znext):
+        # out = xin + 0.5 * drop2(W2 a + b2),  a = swish(h) * drop1,  h = W1 LN(xin) + b1;   dz = 0.5 * drop2-mask * dout
         W1, W2 = P[f"{p}.{name}.fn.fn.net.0.weight"], P[f"{p}.{name}.fn.fn.net.3.weight"]
         dh = _empty(M, 4 * C, dev=dev)
-        gemm(A=dout, lda=C, W=W2, sb_k=4 * C, sb_n=1, C=dh, ldc=4 * C, M=M, N=4 * C, Cin=C, pro=PRO_DROP, pro_alpha=0.5, pro_seed=s2,
-             pro_drop_p=dp, epi=EPI_DSWISH_DROP, aux=f["h"], ldaux=4 * C, seed=s1, drop_p=dp)
-        gemm(wgrad=True, A=f["a"], lda=4 * C, Cin=4 * C, D=dout, ldd=C, N=C, prod=1, alpha=0.5, seed=s2, drop_p=dp, W=None,
-             C=G[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.3.bias"])
+        gemm(A=dz, lda=C, W=W2, sb_k=4 * C, sb_n=1, C=dh, ldc=4 * C, M=M, N=4 * C, Cin=C, epi=EPI_DSWISH_DROP, aux=f["h"], ldaux=4 * C, seed=s1,
+             drop_p=dp)
+        gemm(wgrad=True, A=f["a"], lda=4 * C, Cin=4 * C, D=dz, ldd=C, N=C, W=None, C=G[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C,
+             ldc=0, M=M, dbias=G[f"{p}.{name}.fn.fn.net.3.bias"])
         dln = _empty(M, C, dev=dev)
         gemm(A=dh, lda=4 * C, W=W1, sb_k=C, sb_n=1, C=dln, ldc=C, M=M, N=C, Cin=4 * C)
         gemm(wgrad=True, A=f["xn"], lda=C, Cin=C, D=dh, ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, ldc=0,
              M=M, dbias=G[f"{p}.{name}.fn.fn.net.0.bias"])
-        dxin = _empty(M, C, dev=dev)
-        call("cmgan_ln_bwd", dln, C, xin, C, f["st"], P[f"{p}.{name}.fn.norm.weight"], M, dout, C, res2, C, dxin, C,
-             G[f"{p}.{name}.fn.norm.weight"], G[f"{p}.{name}.fn.norm.bias"])
-        return dxin
+        return ln_bwd(dln, xin, f["st"], f"{p}.{name}.fn.norm", dout, res2, **znext)
 
     # y = LN(x4) * g + b + x
-    dx4 = _empty(M, C, dev=dev)
-    call("cmgan_ln_bwd", dy, C, S["x4"], C, S["st5"], P[f"{p}.post_norm.weight"], M, None, 0, None, 0, dx4, C, G[f"{p}.post_norm.weight"],
-         G[f"{p}.post_norm.bias"])
-    dx3 = ff_bwd(dx4, S["x3"], S["f2"], "ff2", sd[3], sd[4])
+    dx4, dz4 = ln_bwd(dy, S["x4"], S["st5"], f"{p}.post_norm", None, None, zalpha=0.5, zseed=sd[4], zp=dp)
+    dx3, _ = ff_bwd(dx4, dz4, S["x3"], S["f2"], "ff2", sd[3])
     # ---- convolution module: x3 = x2 + W7 swish(bn(d)) + b7
     bn = S["bn"]
     dbn = _empty(M, 2 * C, dev=dev)
@@ -200,18 +209,14 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     gemm(A=dg, lda=4 * C, W=P[f"{p}.conv.net.2.weight"], sb_k=C, sb_n=1, C=dln3, ldc=C, M=M, N=C, Cin=4 * C)
     gemm(wgrad=True, A=S["xn3"], lda=C, Cin=C, D=dg, ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.conv.net.2.weight"], sb_k=1, sb_n=C, ldc=0, M=M,
          dbias=G[f"{p}.conv.net.2.bias"])
-    dx2 = _empty(M, C, dev=dev)
-    call("cmgan_ln_bwd", dln3, C, S["x2"], C, S["st3"], P[f"{p}.conv.net.0.weight"], M, dx3, C, None, 0, dx2, C, G[f"{p}.conv.net.0.weight"],
-         G[f"{p}.conv.net.0.bias"])
-    # ---- attention: x2 = x1 + drop(ctx Wo^T + bo)
+    dx2, dz2 = ln_bwd(dln3, S["x2"], S["st3"], f"{p}.conv.net.0", dx3, None, zalpha=1.0 if da > 0.0 else None, zseed=sd[2], zp=da)
+    if dz2 is None:
+        dz2 = dx2
+    # ---- attention: x2 = x1 + drop(ctx Wo^T + bo);  dz2 = drop-mask * dx2
     dctx = _empty(M, C, dev=dev)
-    if da > 0.0:
-        gemm(A=dx2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C, pro=PRO_DROP, pro_alpha=1.0,
-             pro_seed=sd[2], pro_drop_p=da)
-    else:
-        gemm(A=dx2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C)
-    gemm(wgrad=True, A=S["ctx"], lda=C, Cin=C, D=dx2, ldd=C, N=C, prod=1 if da > 0.0 else 0, alpha=1.0, seed=sd[2], drop_p=da, W=None,
-         C=G[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, ldc=0, M=M, dbias=G[f"{p}.attn.fn.to_out.bias"])
+    gemm(A=dz2, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=C, sb_n=1, C=dctx, ldc=C, M=M, N=C, Cin=C)
+    gemm(wgrad=True, A=S["ctx"], lda=C, Cin=C, D=dz2, ldd=C, N=C, W=None, C=G[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, ldc=0, M=M,
+         dbias=G[f"{p}.attn.fn.to_out.bias"])
     dqkv = _empty(M, 3 * C, dev=dev)
     delta = _empty(M, 4, dev=dev)
     call("cmgan_attention_bwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_bwd", S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv,
@@ -222,8 +227,6 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=dqkv, ldd=3 * C, N=C, W=None, C=G[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
     gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=(dqkv, C), ldd=3 * C, N=2 * C, W=None, C=G[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, ldc=0,
          M=M)
-    dx1 = _empty(M, C, dev=dev)
-    call("cmgan_ln_bwd", dln2, C, S["x1"], C, S["st2"], P[f"{p}.attn.norm.weight"], M, dx2, C, None, 0, dx1, C, G[f"{p}.attn.norm.weight"],
-         G[f"{p}.attn.norm.bias"])
+    dx1, dz1 = ln_bwd(dln2, S["x1"], S["st2"], f"{p}.attn.norm", dx2, None, zalpha=0.5, zseed=sd[1], zp=dp)
     # ---- first feed-forward; the outer residual adds dy
-    return ff_bwd(dx1, S["x"], S["f1"], "ff1", sd[0], sd[1], res2=dy)
+    return ff_bwd(dx1, dz1, S["x"], S["f1"], "ff1", sd[0], res2=dy)[0]

@@ -11,6 +11,8 @@
 //                                                           (cols 2t, 2t+1) equals the A layout (k = t, t+4) under a fixed
 //                                                           permutation of the 8 keys of a k-step, applied to V's rows instead.
 // Operands are rounded to tf32 when staged; accumulation, softmax and the running statistics are fp32.
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 
@@ -92,12 +94,18 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
         }
         __syncthreads();
         if (!warp_active) continue;
+        // a full tile (64 valid keys) runs the straight-line path; the short last tile skips the n-tiles past its end
+        auto tile_body = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int ntv = (nk + 7) >> 3;          // key n-tiles that hold at least one valid key (a short last tile skips the rest)
+        const int rt0 = (KT - nk) >> 3;         // first n-tile of relative distances a valid key can reach
 
         // ---- S = Q K^T
         float sc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            if (!FULL && nt >= ntv) continue;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const float* kp = Ks + (nt * 8 + gq) * LDS_ + t + ks * 8;
@@ -108,6 +116,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
         float* R = Rs[warp];
 #pragma unroll
         for (int nt = 0; nt < RW / 8; ++nt) {
+            if (!FULL && nt < rt0) continue;
             float rc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
@@ -122,11 +131,12 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
         float tmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
+            if (!FULL && nt >= ntv) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = -INFINITY; continue; }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int qrow = gq + (r >> 1) * 8, kcol = nt * 8 + 2 * t + (r & 1);
                 float v = sc[nt][r] + R[qrow * LDR + qrow - kcol + (KT - 1)];
-                if (kcol >= nk) v = -INFINITY;
+                if (!FULL && kcol >= nk) v = -INFINITY;
                 sc[nt][r] = v;
                 tmax[r >> 1] = fmaxf(tmax[r >> 1], v);
             }
@@ -147,16 +157,19 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
 #pragma unroll
         for (int nd = 0; nd < 2; ++nd) { o[nd][0] *= corr[0]; o[nd][1] *= corr[0]; o[nd][2] *= corr[1]; o[nd][3] *= corr[1]; }
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < 8; ++nt) {
+            if (!FULL && nt >= ntv) continue;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const float p = exp2f(sc[nt][r] - mrun[r >> 1]);
                 lrun[r >> 1] += p;
                 sc[nt][r] = tf32r(p);
             }
+        }
         // ---- O += P V.  k-step kk covers keys 8 kk .. 8 kk + 7; A-operand column t <-> key 2t, column t+4 <-> key 2t+1
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+            if (!FULL && kk >= ntv) continue;
             const float pa[4] = {sc[kk][0], sc[kk][2], sc[kk][1], sc[kk][3]};
 #pragma unroll
             for (int nd = 0; nd < 2; ++nd) {
@@ -164,6 +177,8 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
                 mma_tf32(o[nd], pa, vp[0], vp[LDS_]);
             }
         }
+        };
+        if (nk == KT) tile_body(std::true_type{}); else tile_body(std::false_type{});
     }
     if (!warp_active) return;
     // ---- finish: row sums across the quad, normalise, store
@@ -291,6 +306,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
             }
             __syncthreads();
+            auto tile_body = [&](auto full_tag) {       // full tile: straight-line; short last tile: skips the n-tiles past its end
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int ntv = (nk + 7) >> 3;          // key n-tiles with at least one valid key
+            const int rt0 = (KT - nk) >> 3;         // first 8-distance group a valid key can reach (window / block columns >= 64 - nk)
             if (warp_active) {
                 // ---- S = Q K^T, dP = dO V^T
                 float sc[8][4], dp[8][4];
@@ -298,6 +317,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 for (int nt = 0; nt < 8; ++nt) {
                     sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
                     dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+                    if (!FULL && nt >= ntv) continue;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const float* kp = Ks + (nt * 8 + gq) * LDS_ + t + ks * 8;
@@ -309,6 +329,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 // ---- R = Q E_win^T -> smem (this warp's rows, window columns 0..79)
 #pragma unroll
                 for (int nt = 0; nt < RW / 8; ++nt) {
+                    if (!FULL && nt < rt0) continue;
                     float rc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
@@ -321,15 +342,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 __syncwarp();
                 // ---- ds = exp2(s + R_skew - lse) (dp - delta), tf32
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt)
+                for (int nt = 0; nt < 8; ++nt) {
+                    if (!FULL && nt >= ntv) continue;            // sc stays 0: scattered below so that the band of dR is fully rewritten
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int qrow = gq + (r >> 1) * 8, kcol = nt * 8 + 2 * t + (r & 1);
                         const float a = sc[nt][r] + R[qrow * LDRB + qrow - kcol + (KT - 1)];
                         float ds = exp2f(a - ls[r >> 1]) * (dp[nt][r] - dl[r >> 1]);
-                        if (kcol >= nk) ds = 0.f;
+                        if (!FULL && kcol >= nk) ds = 0.f;
                         sc[nt][r] = tf32r(ds);
                     }
+                }
                 __syncwarp();
                 // ---- dR: scatter ds skewed into the same rows; the 16 window columns per row outside the band are zeroed
 #pragma unroll
@@ -348,6 +371,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 // ---- dQ += dS K   (A = dS re-used from the accumulator layout; keys of a k-step permuted, see forward)
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
+                    if (!FULL && kk >= ntv) continue;
                     const float pa[4] = {sc[kk][0], sc[kk][2], sc[kk][1], sc[kk][3]};
 #pragma unroll
                     for (int nd = 0; nd < 2; ++nd) {
@@ -358,6 +382,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 // ---- dQ += dR E_win  (K = 80 distances)
 #pragma unroll
                 for (int kk = 0; kk < RW / 8; ++kk) {
+                    if (!FULL && kk < rt0) continue;             // those distances only pair with keys past the end: dR = 0
                     const float ra[4] = {R[gq * LDRB + kk * 8 + t], R[(gq + 8) * LDRB + kk * 8 + t], R[gq * LDRB + kk * 8 + t + 4],
                                          R[(gq + 8) * LDRB + kk * 8 + t + 4]};
 #pragma unroll
@@ -373,6 +398,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                 const int arow0 = (i0 - j0 - (KT - 1)) - r_acc0 + warp * 32;      // accumulator row of this warp's first distance
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
+                    if (!FULL && warp * 32 + mt * 16 + 16 <= KT - nk) continue;     // block columns below 64 - nk hold zeros only
                     float ec[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
                     for (int ks = 0; ks < QB / 8; ++ks) {
@@ -395,6 +421,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                         }
                 }
             }
+            };
+            if (nk == KT) tile_body(std::true_type{}); else tile_body(std::false_type{});
         }
         if (warp_active) {
 #pragma unroll
@@ -422,7 +450,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
 //   S^T = K Q^T + skew(R2),  R2 = Q_tile E_win^T (64 x 127, computed once per tile by the whole block)
 //   dV += P^T dO,  dK += dS^T Q
 constexpr int LDR2 = 132;
-__global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
+__global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
                                                                const float* __restrict__ dctx, const float* __restrict__ lse,
                                                                const float* __restrict__ delta, float* __restrict__ dqkv) {
     extern __shared__ __align__(16) float smem_kv[];
@@ -459,6 +487,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
     for (int nd = 0; nd < 2; ++nd)
 #pragma unroll
         for (int r = 0; r < 4; ++r) { dk[nd][r] = 0.f; dv[nd][r] = 0.f; }
+    for (int idx = tid; idx < QB * LDR2; idx += 128) R2[idx] = 0.f;     // parts of R2 are skipped for short tiles but may be read (masked)
 
     for (int i0 = 0; i0 < g.L; i0 += QB) {
         const int nq = min(QB, g.L - i0);
@@ -492,6 +521,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
             *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
         }
         __syncthreads();
+        auto tile_body = [&](auto full_tag) {           // full tile: straight-line; short last tile: skips the n-tiles past its end
+        constexpr bool FULL = decltype(full_tag)::value;
         // ---- R2 rows 16 warp .. 16 warp + 15 (queries), all 128 window columns
         {
             float qa[2][4];
@@ -499,8 +530,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
             for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) qa[ks][r] = Qs[(warp * 16 + gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8];
+            // only rows of valid queries and the distances they can reach (columns <= nq + 62) are read back
+            const int ntr = FULL ? 16 : (warp * 16 < nq ? min(16, ((nq + 62) >> 3) + 1) : 0);
 #pragma unroll 4
-            for (int nt = 0; nt < 16; ++nt) {
+            for (int nt = 0; nt < ntr; ++nt) {
                 float rc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
@@ -512,7 +545,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
             }
         }
         __syncthreads();
-        if (!warp_active) continue;
+        if (!warp_active) return;
+        const int ntq = (nq + 7) >> 3;          // query n-tiles with at least one valid query
 
         // ---- S^T = K Q^T, dP^T = V dO^T     (rows = keys gq, gq+8 of this warp; columns = queries of the tile)
         float sc[8][4], dp[8][4];
@@ -520,6 +554,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
         for (int nt = 0; nt < 8; ++nt) {
             sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
             dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+            if (!FULL && nt >= ntq) continue;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const float* qp = Qs + (nt * 8 + gq) * LDS_ + t + ks * 8;
@@ -530,6 +565,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
         }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
+            if (!FULL && nt >= ntq) continue;             // p = ds = 0 there (sc, dp still hold their zeros)
             const float2 l2 = *reinterpret_cast<const float2*>(Ls + nt * 8 + 2 * t);
             const float2 d2 = *reinterpret_cast<const float2*>(Dl + nt * 8 + 2 * t);
 #pragma unroll
@@ -544,6 +580,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
         // ---- dV += P^T dO,  dK += dS^T Q   (A from the accumulator layout; queries of a k-step permuted)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+            if (!FULL && kk >= ntq) continue;
             const float pa[4] = {sc[kk][0], sc[kk][2], sc[kk][1], sc[kk][3]};
             const float sa[4] = {dp[kk][0], dp[kk][2], dp[kk][1], dp[kk][3]};
 #pragma unroll
@@ -554,6 +591,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
                 mma_tf32(dk[nd], sa, qp[0], qp[LDS_]);
             }
         }
+        };
+        if (nq == QB) tile_body(std::true_type{}); else tile_body(std::false_type{});
     }
     if (!warp_active) return;
 #pragma unroll

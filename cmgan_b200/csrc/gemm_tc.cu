@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
         const int ew = warp - 6;
         const int half = EPI8 ? (ew >> 2) : 0;
         constexpr int NH = EPI8 ? 2 : 1;
+        constexpr int PD = EPI8 ? 2 : 1;       // auxiliary-operand prefetch distance in batches (register budget: 128 vs 96 per thread)
+        constexpr int RING = EPI8 ? 4 : 2;     // divides the 4 batches of a slab, so slots are compile-time constants
         float* stg = reinterpret_cast<float*>(base_ptr + (sStg - base)) + ew * 32 * STG_LD;
         const int col4 = (lane & 15) * 4;
         const int rsub = lane >> 4;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
             const long xstep = 2 * ldx;
             // the auxiliary operand does not depend on the accumulator: its first loads are issued before waiting for the MMAs,
             // later batches (4 passes = 8 rows each) one batch ahead of their use
-            float4 ex[2][4];
+            float4 ex[RING][4];                                 // slot = batch index % RING; PD batches of loads in flight
             auto prefetch = [&](int sl, int b4, float4* dst) {
                 const int n = sl * SLAB + col4;
                 if (xbase == nullptr || n >= BN) return;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                 for (int u = 0; u < 4; ++u)
                     if (b4 * 4 + u < npass) dst[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
             };
-            if (half < nslabs) prefetch(half, 0, ex[0]);
+            if (half < nslabs) { prefetch(half, 0, ex[0]); if (PD == 2) prefetch(half, 1, ex[1]); }
             mbar_wait(tfull_bar + 8u * buf, (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * acc_stride + ((uint32_t)(q4 * 32) << 16);
@@ -325,8 +327,8 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                     const uint32_t pstep = (uint32_t)g.N;       // two rows further = N pairs further
 #pragma unroll
                     for (int b4 = 0; b4 < 4; ++b4) {
-                        if (b4 < 3) prefetch(sl, b4 + 1, ex[(b4 + 1) & 1]);
-                        else if (sl + NH < nslabs) prefetch(sl + NH, 0, ex[0]);
+                        if (b4 + PD < 4) prefetch(sl, b4 + PD, ex[(b4 + PD) % RING]);
+                        else if (sl + NH < nslabs) prefetch(sl + NH, b4 + PD - 4, ex[(b4 + PD) % RING]);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int ps = b4 * 4 + u;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                                 ds[0] = (h0 & 0xFFFFu) >= thr16 ? inv_keep : 0.f; ds[1] = (h0 >> 16) >= thr16 ? inv_keep : 0.f;
                                 ds[2] = (h1 & 0xFFFFu) >= thr16 ? inv_keep : 0.f; ds[3] = (h1 >> 16) >= thr16 ? inv_keep : 0.f;
                             }
-                            const float4 xe = ex[b4 & 1][u];
+                            const float4 xe = ex[b4 % RING][u];
                             const float x[4] = {xe.x, xe.y, xe.z, xe.w};
                             if (EPI == CMGAN_EPI_SWISH_DUAL) {
                                 if (cptr) *reinterpret_cast<float4*>(cptr + ps * cstep) = make_float4(v[0], v[1], v[2], v[3]);
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                     }
                 } else if (sl + NH < nslabs) {
                     prefetch(sl + NH, 0, ex[0]);
+                    if (PD == 2) prefetch(sl + NH, 1, ex[1]);
                 }
                 __syncwarp();
             }

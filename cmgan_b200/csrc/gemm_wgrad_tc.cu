@@ -9,7 +9,9 @@
 // Grid: (row chunks) x (taps * k tiles).  Warps 0-3 load (cp.async when the operand needs no transform, else registers with the
 // same prologues as the forward GEMM / the dropout scale on D) and later run the epilogue; warp 8 issues the MMAs.
 // Bias gradient for free: when Cin is not a multiple of 128 the k tile has spare (zero) rows; the row k = Cin is filled with ones
-// instead, so that accumulator row holds sum_m D[m, n] = dbias (otherwise colsum_kernel computes it in a second pass).
+// instead, so that accumulator row holds sum_m D[m, n] = dbias.  Otherwise (Cin % 128 == 0, N <= 128) the CTAs of the first k tile issue
+// a second MMA per row group against a constant all-ones A operand into N extra TMEM columns (every row = dbias).  Only N = 256
+// with Cin % 128 == 0 (not on the hot path) still takes the separate colsum_kernel pass.
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_device.cuh"
@@ -42,7 +44,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
     const int d_stage = RS * NB * 4;
     const uint32_t sA = base;
     const uint32_t sD = base + stages * A_STAGE;
-    const uint32_t bars = sD + stages * d_stage;
+    const uint32_t sOnes = sD + stages * d_stage;           // 4 KB of 1.0f (only read when ones_mma), keeps `bars` 8-byte aligned
+    const uint32_t bars = sOnes + 4096;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (stages + s); };
     const uint32_t tmem_full_bar = bars + 8u * (2 * stages);
@@ -54,6 +57,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
     const long mbeg = (long)blockIdx.x * mch;
     const long mend = mbeg + mch < g.M ? mbeg + mch : g.M;
     const int nst = (int)((mend - mbeg + RS - 1) / RS);
+    const bool ones_mma = g.dbias != nullptr && g.Cin % MO == 0 && 2 * NB <= tmem_cols && blockIdx.y == 0;
+    if (ones_mma) {
+        for (int i = threadIdx.x; i < 1024; i += NTHREADS) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sOnes + 4u * i), "f"(1.0f) : "memory");
+        fence_proxy_async();
+    }
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), NPROD); mbar_init(empty_bar(s), 1); }
@@ -202,6 +210,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                     if (n0 + j < g.N) atomicAdd(dst + (long)(n0 + j) * g.sb_n, acc[j]);
             }
         }
+        if (ones_mma && warp == 0) {              // every row of the second accumulator is the column sum of D
+            for (int n0 = 0; n0 < NB; n0 += 16) {
+                float acc[16];
+                tmem_ld16(trow + (uint32_t)(NB + n0), acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
+                }
+            }
+        }
         tc_fence_before();
         }
     } else {
@@ -218,6 +237,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
                     const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE + kb * 1024, BLK, 512, 1);
                     const uint64_t ddesc = make_desc_sw128(sD + s * d_stage + kb * 1024, BLK, 512, 1);
                     umma_tf32(tmem_base, adesc, ddesc, idesc, (it | kb) != 0 ? 1u : 0u);
+                    if (ones_mma)       // A = ones (4 blocks of 8 rows x 128 B, 1 KB apart): accumulator rows = column sums of D
+                        umma_tf32(tmem_base + (uint32_t)NB, make_desc_sw128(sOnes, 1024, 512, 1), ddesc, idesc, (it | kb) != 0 ? 1u : 0u);
                 }
                 umma_commit(empty_bar(s));
             }
@@ -287,11 +308,12 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     if (!wgrad_tc_supported(a)) return 1;
     const int NB = a->N;
     const int d_stage = RS * NB * 4;
-    int stages = (100 * 1024 - 2048) / (A_STAGE + d_stage);
+    int stages = (100 * 1024 - 2048 - 4096) / (A_STAGE + d_stage);
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
+    const bool ones_mma = a->dbias && a->Cin % MO == 0 && NB <= 128;      // 2 N columns, two co-resident CTAs -> N <= 128
     int tmem_cols = 32;
-    while (tmem_cols < NB) tmem_cols <<= 1;
+    while (tmem_cols < (ones_mma ? 2 * NB : NB)) tmem_cols <<= 1;
     const int ktiles = (a->Cin + MO - 1) / MO;
     const int ytiles = ktiles * a->ntaps;
     // rows per CTA: enough CTAs for ~3 waves of 296 resident CTAs, at least 16 stages per CTA to amortise the TMEM round trip
@@ -301,7 +323,7 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     mch = ((mch + RS - 1) / RS) * RS;
     if (mch < 16 * RS) mch = 16 * RS;
     dim3 grid((unsigned)((a->M + mch - 1) / mch), (unsigned)ytiles);
-    const size_t smem = (size_t)stages * (A_STAGE + d_stage) + 1024 + 8 * (2 * stages + 2) + 16;
+    const size_t smem = (size_t)stages * (A_STAGE + d_stage) + 4096 + 1024 + 8 * (2 * stages + 2) + 16;
     const bool aa = a->pro == CMGAN_PRO_NONE, da = a->prod == 0;
     int rc;
     if (aa && da) rc = launch<true, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
@@ -309,7 +331,7 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     else if (da) rc = launch<false, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     else rc = launch<false, false>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     if (rc) return rc;
-    if (a->dbias && a->Cin % MO == 0) {       // no spare accumulator row for the fused column sum
+    if (a->dbias && a->Cin % MO == 0 && !ones_mma) {       // no spare accumulator row, too wide for the ones MMA
         const int rpb = 64 * (256 / a->N > 0 ? 256 / a->N : 1);     // ~64 rows per thread -> thousands of blocks
         colsum_kernel<<<cdiv(a->M, rpb), 256, 0, st>>>(a->D, a->ldd, a->M, a->N, a->prod, a->alpha, a->seed, a->drop_thr, a->inv_keep, rpb, a->dbias, a->seed_dev);
         return cmgan_check_launch("colsum_kernel");

@@ -54,12 +54,18 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const flo
                               const float2* __restrict__ stats, const float* __restrict__ gamma, long M,
                               const float* __restrict__ res, long ldr, const float* __restrict__ res2, long ldr2,
                               float* __restrict__ dx, long lddx,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp) {
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp,
+                              float* __restrict__ dz, long lddz, float zalpha, unsigned long long zseed, unsigned zthr, float zinv_keep,
+                              const unsigned long long* __restrict__ seed_dev) {
     __shared__ float sg[8][LN_C], sb[8][LN_C];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     long r0 = ((long)blockIdx.x * nw + warp) * rows_per_warp;
     float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + lane);
     float2 ag = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
+    // optional second output dz = zalpha * dropmask(zseed) * dx: the gradient entering the next residual branch, whose forward output
+    // went through dropout (mask regenerated from the element index row * 64 + channel, as in the GEMM epilogue that applied it)
+    const uint32_t zs32 = dz ? cmgan_seed32(zseed + (seed_dev ? __ldg(seed_dev) : 0ull)) : 0u;
+    const uint32_t zt16 = zthr >> 16;
     for (int i = 0; i < rows_per_warp; ++i) {
         long row = r0 + i;
         if (row >= M) break;
@@ -74,6 +80,15 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const flo
         if (res) { float2 r = __ldg(reinterpret_cast<const float2*>(res + row * ldr) + lane); o.x += r.x; o.y += r.y; }
         if (res2) { float2 r = __ldg(reinterpret_cast<const float2*>(res2 + row * ldr2) + lane); o.x += r.x; o.y += r.y; }
         reinterpret_cast<float2*>(dx + row * lddx)[lane] = o;
+        if (dz) {
+            float s0 = zalpha, s1 = zalpha;
+            if (zthr) {
+                const uint32_t h = cmgan_pair_hash(zs32, (uint64_t)row * (LN_C / 2) + lane);
+                s0 = (h & 0xFFFFu) >= zt16 ? zalpha * zinv_keep : 0.f;
+                s1 = (h >> 16) >= zt16 ? zalpha * zinv_keep : 0.f;
+            }
+            reinterpret_cast<float2*>(dz + row * lddz)[lane] = make_float2(o.x * s0, o.y * s1);
+        }
         ag.x += d.x * xh0; ag.y += d.y * xh1; ab.x += d.x; ab.y += d.y;
     }
     sg[warp][2 * lane] = ag.x; sg[warp][2 * lane + 1] = ag.y;
@@ -275,16 +290,35 @@ CMGAN_API int cmgan_ln_apply(const float* x, long long ldx, long long M, const f
     return cmgan_check_launch("ln_apply_kernel");
 }
 
+static int ln_bwd_launch(const float* dy, long long lddy, const float* x, long long ldx, const float* stats, const float* gamma, long long M,
+                         const float* res, long long ldr, const float* res2, long long ldr2, float* dx, long long lddx, float* dgamma,
+                         float* dbeta, float* dz, long long lddz, float zalpha, unsigned long long zseed, unsigned zthr, float zinv_keep,
+                         const unsigned long long* seed_dev, void* stream, const char* who) {
+    CMGAN_REQUIRE(dy && x && stats && gamma && dx && dgamma && dbeta, "%s: null pointer", who);
+    CMGAN_REQUIRE(lddy % 2 == 0 && ldx % 2 == 0 && lddx % 2 == 0 && ldr % 2 == 0 && ldr2 % 2 == 0 && lddz % 2 == 0, "%s: odd leading dimension", who);
+    if (M == 0) return 0;
+    const int rpw = 16;
+    ln_bwd_kernel<<<cdiv(M, 8 * rpw), 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, reinterpret_cast<const float2*>(stats), gamma, M, res, ldr,
+                                                                     res2, ldr2, dx, lddx, dgamma, dbeta, rpw, dz, lddz, zalpha, zseed, zthr,
+                                                                     zinv_keep, seed_dev);
+    return cmgan_check_launch("ln_bwd_kernel");
+}
+
 CMGAN_API int cmgan_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* stats,
                            const float* gamma, long long M, const float* res, long long ldr, const float* res2, long long ldr2,
                            float* dx, long long lddx, float* dgamma, float* dbeta, void* stream) {
-    CMGAN_REQUIRE(dy && x && stats && gamma && dx && dgamma && dbeta, "cmgan_ln_bwd: null pointer");
-    CMGAN_REQUIRE(lddy % 2 == 0 && ldx % 2 == 0 && lddx % 2 == 0 && ldr % 2 == 0 && ldr2 % 2 == 0, "cmgan_ln_bwd: odd leading dimension");
-    if (M == 0) return 0;
-    const int rpw = 16;
-    ln_bwd_kernel<<<cdiv(M, 8 * rpw), 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, reinterpret_cast<const float2*>(stats),
-                                                                     gamma, M, res, ldr, res2, ldr2, dx, lddx, dgamma, dbeta, rpw);
-    return cmgan_check_launch("ln_bwd_kernel");
+    return ln_bwd_launch(dy, lddy, x, ldx, stats, gamma, M, res, ldr, res2, ldr2, dx, lddx, dgamma, dbeta, nullptr, 0, 1.f, 0ull, 0u, 1.f, nullptr,
+                         stream, "cmgan_ln_bwd");
+}
+
+// same, plus dz = alpha * dropout_scale(seed; element index row * 64 + c) * dx  (thr = p * 2^32, 0 = no dropout)
+CMGAN_API int cmgan_ln_bwd_drop(const float* dy, long long lddy, const float* x, long long ldx, const float* stats, const float* gamma,
+                                long long M, const float* res, long long ldr, const float* res2, long long ldr2, float* dx, long long lddx,
+                                float* dgamma, float* dbeta, float* dz, long long lddz, float alpha, unsigned long long seed, unsigned int thr,
+                                float inv_keep, const unsigned long long* seed_dev, void* stream) {
+    CMGAN_REQUIRE(dz != nullptr, "cmgan_ln_bwd_drop: dz is null");
+    return ln_bwd_launch(dy, lddy, x, ldx, stats, gamma, M, res, ldr, res2, ldr2, dx, lddx, dgamma, dbeta, dz, lddz, alpha, seed, thr, inv_keep,
+                         seed_dev, stream, "cmgan_ln_bwd_drop");
 }
 
 static int norm_threads(int C) { return C <= 256 ? 256 : C; }

@@ -30,6 +30,7 @@ int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream);
 int cmgan_ln_stats(const float* x, long long ldx, long long M, float* stats, void* stream);
 int cmgan_ln_apply(const float* x, long long ldx, long long M, const float* gamma, const float* beta, const float* res, long long ldr, float* y, long long ldy, float* stats, int round_tf32, void* stream);
 int cmgan_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* stats, const float* gamma, long long M, const float* res, long long ldr, const float* res2, long long ldr2, float* dx, long long lddx, float* dgamma, float* dbeta, void* stream);
+int cmgan_ln_bwd_drop(const float* dy, long long lddy, const float* x, long long ldx, const float* stats, const float* gamma, long long M, const float* res, long long ldr, const float* res2, long long ldr2, float* dx, long long lddx, float* dgamma, float* dbeta, float* dz, long long lddz, float alpha, unsigned long long seed, unsigned int thr, float inv_keep, const unsigned long long* seed_dev, void* stream);
 int cmgan_norm_stats(const float* x, long long ldx, int G, long long rows_per_group, int C, double* sums, void* stream);
 int cmgan_norm_finalize(const double* sums, long long n, int G, int C, int mode, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float* scale, float* shift, float* mean_out, float* rstd_out, long long tstride, void* stream);
 int cmgan_norm_bwd_reduce(const float* x, long long ldx, const float* dact, long long ldd, int G, long long rows_per_group, int C, int act, const float* scale, const float* shift, const float* mean, const float* rstd, long long tstride, const float* slope, double* S, float* dslope, void* stream);
