@@ -15,8 +15,13 @@
 
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
+#include "tc_ptx.cuh"
 
 namespace {
+using cmgan_tc::cp_async16;
+using cmgan_tc::cp_async_commit;
+using cmgan_tc::cp_async_wait;
+using cmgan_tc::smem_u32;
 
 constexpr int D = 16, H = 4, CQ = 64, LDQ = 192;
 constexpr int QB = 64;            // queries per block (4 warps x 16)
@@ -41,9 +46,33 @@ __device__ __forceinline__ void mma_tf32(float c[4], const float a[4], float b0,
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// One tile of operands, staged asynchronously (cp.async, 16 B, zero fill past the end of the sequence) one tile ahead of its use:
+//   As, Bs : 64 rows x 16 floats (row stride LDS_) of two row operands (K and V, or Q and dO), rows first .. first + 63 of the sequence
+//   Es     : the relative-position rows E[clamp(rfirst + w)] for w < EROWS
+// Raw fp32 lands in shared memory; the tensor cores read the tf32 bits of it (low mantissa bits ignored).
+constexpr int EROWS = EW + 1;     // 128: every window row an n-tile can touch
+constexpr int TILE_FLOATS = 2 * KT * LDS_ + EROWS * LDS_;
+__device__ __forceinline__ void stage_tile_async(float* buf, const float* __restrict__ a_src, int a_ld, const float* __restrict__ b_src, int b_ld,
+                                                 long base, long tok_stride, int first, int L, const float* __restrict__ E, int rfirst, int tid) {
+    const uint32_t sa = smem_u32(buf), sb = sa + KT * LDS_ * 4, se = sb + KT * LDS_ * 4;
+    for (int idx = tid; idx < KT * 4; idx += 128) {
+        const int r = idx >> 2, q4 = idx & 3;
+        const bool ok = first + r < L;
+        const long row = base + (long)(ok ? first + r : 0) * tok_stride;
+        cp_async16(sa + (r * LDS_ + q4 * 4) * 4, a_src + row * a_ld + q4 * 4, ok ? 16u : 0u);
+        cp_async16(sb + (r * LDS_ + q4 * 4) * 4, b_src + row * b_ld + q4 * 4, ok ? 16u : 0u);
+    }
+    for (int idx = tid; idx < EROWS * 4; idx += 128) {
+        const int w = idx >> 2, q4 = idx & 3;
+        const int e = clampi(rfirst + w, -MAXPOS, MAXPOS) + MAXPOS;
+        cp_async16(se + (w * LDS_ + q4 * 4) * 4, E + e * D + q4 * 4, 16u);
+    }
+}
+
 __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
                                                            float* __restrict__ ctx, float* __restrict__ lse) {
-    __shared__ __align__(16) float Ks[KT * LDS_], Vs[KT * LDS_], Es[EW * LDS_ + 4 * LDS_], Rs[4][16 * LDR];
+    extern __shared__ __align__(16) float smem_fwd[];          // tile buffers [2][TILE_FLOATS] | Rs[4][16 * LDR]
+    float* Rs0 = smem_fwd + 2 * TILE_FLOATS;
     const int s = blockIdx.x / H, h = blockIdx.x % H;
     const int i0 = blockIdx.y * QB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
@@ -69,29 +98,22 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
         for (int r = 0; r < 4; ++r) o[nd][r] = 0.f;
     float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};     // rows gq and gq+8 (lrun: this lane's partial sum)
 
-    for (int j0 = 0; j0 < g.L; j0 += KT) {
+    const float* ksrc = qkv + h * D + CQ;
+    const float* vsrc = qkv + h * D + 2 * CQ;
+    // window row w <-> relative distance r = (i0 - j0 - (KT - 1)) + w
+    stage_tile_async(smem_fwd, ksrc, LDQ, vsrc, LDQ, base, g.tok_stride, 0, g.L, E, i0 - (KT - 1), tid);
+    cp_async_commit();
+    for (int j0 = 0, it = 0; j0 < g.L; j0 += KT, ++it) {
         const int nk = min(KT, g.L - j0);
-        __syncthreads();
-        // ---- stage K, V (64 rows) and the E window (127 rows), rounded to tf32
-        for (int idx = tid; idx < KT * 4; idx += 128) {
-            const int r = idx >> 2, q4 = idx & 3;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (r < nk) {
-                const float* p = qkv + (base + (long)(j0 + r) * g.tok_stride) * LDQ + h * D;
-                kv = __ldg(reinterpret_cast<const float4*>(p + CQ) + q4);
-                vv = __ldg(reinterpret_cast<const float4*>(p + 2 * CQ) + q4);
-            }
-            *reinterpret_cast<float4*>(Ks + r * LDS_ + q4 * 4) = make_float4(tf32r(kv.x), tf32r(kv.y), tf32r(kv.z), tf32r(kv.w));
-            *reinterpret_cast<float4*>(Vs + r * LDS_ + q4 * 4) = make_float4(tf32r(vv.x), tf32r(vv.y), tf32r(vv.z), tf32r(vv.w));
-        }
-        // window row w <-> relative distance r = (i0 - j0 - (KT - 1)) + w;  rows beyond EW - 1 (padding of the last n-tile) repeat the edge
-        const int rfirst = i0 - j0 - (KT - 1);
-        for (int idx = tid; idx < (EW + 4) * 4; idx += 128) {
-            const int w = idx >> 2, q4 = idx & 3;
-            const int e = clampi(rfirst + w, -MAXPOS, MAXPOS) + MAXPOS;
-            const float4 ev = __ldg(reinterpret_cast<const float4*>(E + e * D) + q4);
-            *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
-        }
+        const float* Ks = smem_fwd + (it & 1) * TILE_FLOATS;
+        const float* Vs = Ks + KT * LDS_;
+        const float* Es = Vs + KT * LDS_;
+        __syncthreads();                              // every warp is done with the buffer the next tile is staged into
+        if (j0 + KT < g.L)
+            stage_tile_async(smem_fwd + ((it + 1) & 1) * TILE_FLOATS, ksrc, LDQ, vsrc, LDQ, base, g.tok_stride, j0 + KT, g.L, E,
+                             i0 - (j0 + KT) - (KT - 1), tid);
+        cp_async_commit();
+        cp_async_wait<1>();                           // this tile has landed (the group just committed may still be in flight)
         __syncthreads();
         if (!warp_active) continue;
         // a full tile (64 valid keys) runs the straight-line path; the short last tile skips the n-tiles past its end
@@ -113,7 +135,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
             }
         }
         // ---- R = Q E^T over this warp's 80 distances: window rows [16 w, 16 w + 80)   (r = iw - j0 - 63 + c)
-        float* R = Rs[warp];
+        float* R = Rs0 + warp * 16 * LDR;
 #pragma unroll
         for (int nt = 0; nt < RW / 8; ++nt) {
             if (!FULL && nt < rt0) continue;
@@ -215,7 +237,7 @@ constexpr float LN2 = 0.6931471805599453f;
 //                                           64 queries x 127 distances; a warp writes only its own 16 rows)
 //   dEw = dR^T Q                            128 x 16 per block and key tile; each warp owns 32 distances -> plain adds into the
 //                                           block accumulator (no atomics: shared fp32 atomics are CAS loops)
-// dynamic smem: Ks | Vs | Es | Rb[64 x LDRB] | Qs[64 x 20] | dEs[(Lpad + 64) x 16]
+// dynamic smem: (Ks | Vs | Es)[2] | Rb[64 x LDRB] | Qs[64 x 20] | dEs[(Lpad + 64) x 16]
 constexpr int LDRB = 136;
 __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
                                                               const float* __restrict__ ctx, const float* __restrict__ dctx,
@@ -223,10 +245,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                                                               float* __restrict__ delta, float* __restrict__ dqkv,
                                                               float* __restrict__ dE) {
     extern __shared__ __align__(16) float smem_dq[];
-    float* Ks = smem_dq;
-    float* Vs = Ks + KT * LDS_;
-    float* Es = Vs + KT * LDS_;
-    float* Rb = Es + (EW + 4) * LDS_;
+    float* Rb = smem_dq + 2 * TILE_FLOATS;            // after the two K / V / E tile buffers
     float* Qs = Rb + QB * LDRB;
     float* dEs = Qs + QB * LDS_;
     const int i0 = blockIdx.y * QB;
@@ -240,6 +259,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
     float* R = Rb + warp * 16 * LDRB + warp * 16;     // this warp's rows; its 80-distance window starts at block column 16 warp
     float* Qw = Qs + warp * 16 * LDS_;
 
+    // tiles are staged one ahead, across item boundaries: (item, j0) -> (item, j0 + 64) or (next item, 0)
+    auto stage = [&](int item, int j0, int slot) {
+        const int s = item / H, h = item % H;
+        stage_tile_async(smem_dq + slot * TILE_FLOATS, qkv + h * D + CQ, LDQ, qkv + h * D + 2 * CQ, LDQ, seq_base(g, s), g.tok_stride, j0, g.L, E,
+                         i0 - j0 - (KT - 1), tid);
+    };
+    if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0, 0);
+    cp_async_commit();
+    int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int s = item / H, h = item % H;
         const long base = seq_base(g, s);
@@ -287,25 +315,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
 #pragma unroll
                     for (int r = 0; r < 4; ++r) Qw[(gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8] = qa[ks][r];
             }
-            for (int idx = tid; idx < KT * 4; idx += 128) {
-                const int r = idx >> 2, q4 = idx & 3;
-                float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-                if (r < nk) {
-                    const float* p = qkv + (base + (long)(j0 + r) * g.tok_stride) * LDQ + h * D;
-                    kv = __ldg(reinterpret_cast<const float4*>(p + CQ) + q4);
-                    vv = __ldg(reinterpret_cast<const float4*>(p + 2 * CQ) + q4);
-                }
-                *reinterpret_cast<float4*>(Ks + r * LDS_ + q4 * 4) = make_float4(tf32r(kv.x), tf32r(kv.y), tf32r(kv.z), tf32r(kv.w));
-                *reinterpret_cast<float4*>(Vs + r * LDS_ + q4 * 4) = make_float4(tf32r(vv.x), tf32r(vv.y), tf32r(vv.z), tf32r(vv.w));
-            }
-            const int rfirst = i0 - j0 - (KT - 1);
-            for (int idx = tid; idx < (EW + 4) * 4; idx += 128) {
-                const int w = idx >> 2, q4 = idx & 3;
-                const int e = clampi(rfirst + w, -MAXPOS, MAXPOS) + MAXPOS;
-                const float4 ev = __ldg(reinterpret_cast<const float4*>(E + e * D) + q4);
-                *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
-            }
+            if (j0 + KT < g.L) stage(item, j0 + KT, (it + 1) & 1);
+            else if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, 0, (it + 1) & 1);
+            cp_async_commit();
+            cp_async_wait<1>();
             __syncthreads();
+            const float* Ks = smem_dq + (it & 1) * TILE_FLOATS;
+            const float* Vs = Ks + KT * LDS_;
+            const float* Es = Vs + KT * LDS_;
+            ++it;
             auto tile_body = [&](auto full_tag) {       // full tile: straight-line; short last tile: skips the n-tiles past its end
             constexpr bool FULL = decltype(full_tag)::value;
             const int ntv = (nk + 7) >> 3;          // key n-tiles with at least one valid key
@@ -450,16 +468,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
 //   S^T = K Q^T + skew(R2),  R2 = Q_tile E_win^T (64 x 127, computed once per tile by the whole block)
 //   dV += P^T dO,  dK += dS^T Q
 constexpr int LDR2 = 132;
-__global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
+__global__ void __launch_bounds__(128, 3) attn_bwd_dkv_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
                                                                const float* __restrict__ dctx, const float* __restrict__ lse,
                                                                const float* __restrict__ delta, float* __restrict__ dqkv) {
     extern __shared__ __align__(16) float smem_kv[];
-    float* Qs = smem_kv;
-    float* Os = Qs + QB * LDS_;
-    float* Es = Os + QB * LDS_;
-    float* R2 = Es + (EW + 4) * LDS_;
-    float* Ls = R2 + QB * LDR2;
-    float* Dl = Ls + QB;
+    float* R2 = smem_kv + 2 * TILE_FLOATS;            // after the two Q / dO / E tile buffers
+    float* LD = R2 + QB * LDR2;                       // [2][lse (64) | delta (64)]
     const int s = blockIdx.x / H, h = blockIdx.x % H;
     const int j0 = blockIdx.y * KT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
@@ -479,7 +493,7 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* _
                 kv = __ldg(p + CQ);
                 vv = __ldg(p + 2 * CQ);
             }
-            ka[ks][r] = tf32r(kv);
+            ka[ks][r] = tf32r(kv * SCALE_LOG2E);       // the logit scale rides on K: Q is staged raw by cp.async
             va[ks][r] = tf32r(vv);
         }
     float dk[2][4], dv[2][4];
@@ -489,38 +503,31 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* _
         for (int r = 0; r < 4; ++r) { dk[nd][r] = 0.f; dv[nd][r] = 0.f; }
     for (int idx = tid; idx < QB * LDR2; idx += 128) R2[idx] = 0.f;     // parts of R2 are skipped for short tiles but may be read (masked)
 
-    for (int i0 = 0; i0 < g.L; i0 += QB) {
+    const float* qsrc = qkv + h * D;
+    const float* osrc = dctx + h * D;
+    // lse / delta of the tile's queries: 4-byte cp.async (zero fill past the end; those queries are masked explicitly)
+    auto stage = [&](int i0, int slot) {
+        stage_tile_async(smem_kv + slot * TILE_FLOATS, qsrc, LDQ, osrc, CQ, base, g.tok_stride, i0, g.L, E, i0 - j0 - (KT - 1), tid);
+        const int r = tid & 63;
+        const bool ok = i0 + r < g.L;
+        const long rr = base + (long)(ok ? i0 + r : 0) * g.tok_stride;
+        const float* src = (tid < 64 ? lse : delta) + rr * H + h;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(LD + slot * 2 * QB + tid)), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+    };
+    stage(0, 0);
+    cp_async_commit();
+    for (int i0 = 0, it = 0; i0 < g.L; i0 += QB, ++it) {
         const int nq = min(QB, g.L - i0);
+        __syncthreads();                                  // every warp is done with the buffers the next tile is staged into (and with R2)
+        if (i0 + QB < g.L) stage(i0 + QB, (it + 1) & 1);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        for (int idx = tid; idx < QB * 4; idx += 128) {
-            const int r = idx >> 2, q4 = idx & 3;
-            float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), ov = qv;
-            if (r < nq) {
-                const long rr = base + (long)(i0 + r) * g.tok_stride;
-                qv = __ldg(reinterpret_cast<const float4*>(qkv + rr * LDQ + h * D) + q4);
-                ov = __ldg(reinterpret_cast<const float4*>(dctx + rr * CQ + h * D) + q4);
-            }
-            *reinterpret_cast<float4*>(Qs + r * LDS_ + q4 * 4) = make_float4(tf32r(qv.x * SCALE_LOG2E), tf32r(qv.y * SCALE_LOG2E),
-                                                                             tf32r(qv.z * SCALE_LOG2E), tf32r(qv.w * SCALE_LOG2E));
-            *reinterpret_cast<float4*>(Os + r * LDS_ + q4 * 4) = make_float4(tf32r(ov.x), tf32r(ov.y), tf32r(ov.z), tf32r(ov.w));
-        }
-        for (int r = tid; r < QB; r += 128) {
-            float l = INFINITY, d = 0.f;                        // queries past the end: p = exp2(-inf) = 0
-            if (r < nq) {
-                const long rr = base + (long)(i0 + r) * g.tok_stride;
-                l = __ldg(lse + rr * H + h);
-                d = __ldg(delta + rr * H + h);
-            }
-            Ls[r] = l; Dl[r] = d;
-        }
-        const int rfirst = i0 - j0 - (KT - 1);                  // window column c <-> distance rfirst + c,  c = il - jl + 63
-        for (int idx = tid; idx < (EW + 4) * 4; idx += 128) {
-            const int w = idx >> 2, q4 = idx & 3;
-            const int e = clampi(rfirst + w, -MAXPOS, MAXPOS) + MAXPOS;
-            const float4 ev = __ldg(reinterpret_cast<const float4*>(E + e * D) + q4);
-            *reinterpret_cast<float4*>(Es + w * LDS_ + q4 * 4) = make_float4(tf32r(ev.x), tf32r(ev.y), tf32r(ev.z), tf32r(ev.w));
-        }
-        __syncthreads();
+        const float* Qs = smem_kv + (it & 1) * TILE_FLOATS;       // window column c <-> distance (i0 - j0 - 63) + c,  c = il - jl + 63
+        const float* Os = Qs + QB * LDS_;
+        const float* Es = Os + QB * LDS_;
+        const float* Ls = LD + (it & 1) * 2 * QB;
+        const float* Dl = Ls + QB;
         auto tile_body = [&](auto full_tag) {           // full tile: straight-line; short last tile: skips the n-tiles past its end
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- R2 rows 16 warp .. 16 warp + 15 (queries), all 128 window columns
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* _
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) qa[ks][r] = Qs[(warp * 16 + gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8];
+                for (int r = 0; r < 4; ++r) qa[ks][r] = Qs[(warp * 16 + gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8] * SCALE_LOG2E;
             // only rows of valid queries and the distances they can reach (columns <= nq + 62) are read back
             const int ntr = FULL ? 16 : (warp * 16 < nq ? min(16, ((nq + 62) >> 3) + 1) : 0);
 #pragma unroll 4
@@ -572,7 +579,8 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* _
             for (int r = 0; r < 4; ++r) {
                 const int jl = warp * 16 + gq + (r >> 1) * 8, il = nt * 8 + 2 * t + (r & 1);
                 const float a = sc[nt][r] + R2[il * LDR2 + il - jl + (KT - 1)];
-                const float p = exp2f(a - ((r & 1) ? l2.y : l2.x));
+                float p = exp2f(a - ((r & 1) ? l2.y : l2.x));
+                if (!FULL && il >= nq) p = 0.f;          // queries past the end of the sequence (their lse was zero-filled)
                 sc[nt][r] = tf32r(p);
                 dp[nt][r] = tf32r(p * (dp[nt][r] - ((r & 1) ? d2.y : d2.x)));
             }
@@ -602,7 +610,7 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dkv_mma_kernel(const float* _
         float* p = dqkv + (base + (long)j * g.tok_stride) * LDQ + h * D + 2 * t;
 #pragma unroll
         for (int nd = 0; nd < 2; ++nd) {
-            *reinterpret_cast<float2*>(p + CQ + nd * 8) = make_float2(LN2 * dk[nd][hrow * 2], LN2 * dk[nd][hrow * 2 + 1]);
+            *reinterpret_cast<float2*>(p + CQ + nd * 8) = make_float2(0.25f * dk[nd][hrow * 2], 0.25f * dk[nd][hrow * 2 + 1]);      // Q was staged unscaled
             *reinterpret_cast<float2*>(p + 2 * CQ + nd * 8) = make_float2(dv[nd][hrow * 2], dv[nd][hrow * 2 + 1]);
         }
     }
@@ -617,7 +625,14 @@ CMGAN_API int cmgan_attention_fwd_tf32(const float* qkv, const float* E, int B, 
     SeqGeom g = make_seq_geom(B, T, F, axis);
     if (g.n_seq == 0 || g.L == 0) return 0;
     dim3 grid(g.n_seq * H, cdiv(g.L, QB));
-    attn_fwd_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, g, E, ctx, lse);
+    const int smem = (2 * TILE_FLOATS + 4 * 16 * LDR) * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        CMGAN_REQUIRE(e == cudaSuccess, "cmgan_attention_fwd_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    attn_fwd_mma_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, g, E, ctx, lse);
     return cmgan_check_launch("attn_fwd_mma_kernel");
 }
 
@@ -630,8 +645,8 @@ CMGAN_API int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const f
     if (g.n_seq == 0 || g.L == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int ntile = cdiv(g.L, QB), Lpad = ntile * KT;
-    const int smem_dq = (2 * KT * LDS_ + (EW + 4) * LDS_ + QB * LDRB + QB * LDS_ + (Lpad + 64) * D) * (int)sizeof(float);
-    const int smem_kv = (2 * QB * LDS_ + (EW + 4) * LDS_ + QB * LDR2 + 2 * QB) * (int)sizeof(float);
+    const int smem_dq = (2 * TILE_FLOATS + QB * LDRB + QB * LDS_ + (Lpad + 64) * D) * (int)sizeof(float);
+    const int smem_kv = (2 * TILE_FLOATS + QB * LDR2 + 4 * QB) * (int)sizeof(float);
     CMGAN_REQUIRE(smem_dq <= 227 * 1024, "cmgan_attention_bwd_tf32: sequence length %d too long for the shared dE accumulator", g.L);
     static int smem_dq_set = 0;
     static bool kv_set = false;
