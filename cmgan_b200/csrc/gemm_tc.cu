@@ -19,6 +19,8 @@
 // The weight operand is re-tiled once per call by pack_b_kernel into the scratch the caller passes (any source layout:
 // Linear (N,K), Conv2d (N,C,kh,kw), and the transposed forms used for data gradients).
 // All waits are bounded (a protocol bug traps instead of hanging the GPU).
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched from the driver at run time)
+
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_device.cuh"
@@ -56,11 +58,11 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
     out[(chunk * BN + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
 }
 
-struct TcCfg { int BN, stages, tmem_cols, resident, ntiles; };
+struct TcCfg { int BN, stages, tmem_cols, resident, ntiles, tma; };
 
 template <bool ASYNC_A, bool EPI8, int EPI>
 __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI8) ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
-                                                                    const TcCfg cfg) {
+                                                                    const TcCfg cfg, const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), NPROD + (cfg.resident ? 0 : 1)); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), (cfg.tma ? 1 : NPROD) + (cfg.resident ? 0 : 1)); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8u * b, 1); mbar_init(tempty_bar + 8u * b, EPI8 ? 8 : 4); }
         mbar_init(bready_bar, 1);
         fence_barrier_init();
@@ -107,7 +109,21 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
         for (int i = 0; i < 8; ++i) { const int r = rr + 16 * i; dst_off[i] = r * 128 + ((c ^ (r & 7)) << 4); }
         const long total = (long)my_tiles * nchunks;
 
-        if (ASYNC_A) {
+        if (ASYNC_A && cfg.tma) {
+            // dense row-major A (no gather): one thread drives TMA, a 128-row x 32-float box per K chunk written straight into the
+            // SWIZZLE_128B layout (rows past M are zero-filled by the unit); every stage of the ring can be in flight
+            if (tid == 0) {
+                for (long q = 0; q < total; ++q) {
+                    const int lt = (int)(q / nchunks), ch = (int)(q - (long)lt * nchunks);
+                    const int s = (int)(q % stages);
+                    const uint32_t par = (uint32_t)((q / stages) & 1);
+                    mbar_wait(empty_bar(s), par ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)A_STAGE_BYTES);
+                    tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, ch * KC, (blockIdx.x + lt * gridDim.x) * BM, full_bar(s));
+                }
+            }
+            __syncwarp();
+        } else if (ASYNC_A) {
             const int LAG = stages >= 3 ? 2 : 1;
             long rowoff[8];
             RowInfo ri[8];
@@ -407,15 +423,18 @@ int tc_supported(const CmganGemmArgs* a) {
 
 int g_num_sms = 0;
 
+using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 template <bool ASYNC_A, bool EPI8, int EPI>
-int launch_variant(const CmganGemmArgs& a, const TcCfg& cfg, int grid, size_t smem, cudaStream_t st) {
+int launch_variant(const CmganGemmArgs& a, const TcCfg& cfg, int grid, size_t smem, cudaStream_t st, const CUtensorMap& tm) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) { cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
         attr_set = true;
     }
-    gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI><<<grid, EPI8 ? NTHREADS8 : NTHREADS4, smem, st>>>(a, a.ws, cfg);
+    gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI><<<grid, EPI8 ? NTHREADS8 : NTHREADS4, smem, st>>>(a, a.ws, cfg, tm);
     return 0;
 }
 
@@ -449,6 +468,31 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    // dense row-major A without prologue: describe it to TMA (box = 32 floats x 128 rows, SWIZZLE_128B, zero fill out of bounds)
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    cfg.tma = 0;
+    if (a->pro == CMGAN_PRO_NONE && !a->conv && a->ntaps == 1 && a->lda % 4 == 0) {
+        static PFN_encodeTiled encode = nullptr;
+        static bool tried = false;
+        if (!tried) {
+            tried = true;
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                encode = reinterpret_cast<PFN_encodeTiled>(fn);
+        }
+        if (encode) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)a->Cin, (cuuint64_t)a->M};
+            const cuuint64_t gstride[1] = {(cuuint64_t)a->lda * sizeof(float)};
+            const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BM};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->A + a->tap_off[0]), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) cfg.tma = 1;
+        }
+    }
     long total = (long)nchunks * cfg.BN * KC;
     pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
     if (cmgan_check_launch("pack_b_kernel")) return -1;
@@ -457,9 +501,9 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     int rc = -2;
 #define CMGAN_TC_LAUNCH(E)                                                                                            \
     case E:                                                                                                           \
-        rc = variant == 0   ? launch_variant<false, true, E>(*a, cfg, grid, smem, st)                                 \
-             : variant == 1 ? launch_variant<true, true, E>(*a, cfg, grid, smem, st)                                  \
-                            : launch_variant<true, false, E>(*a, cfg, grid, smem, st);                                \
+        rc = variant == 0   ? launch_variant<false, true, E>(*a, cfg, grid, smem, st, tm)                             \
+             : variant == 1 ? launch_variant<true, true, E>(*a, cfg, grid, smem, st, tm)                              \
+                            : launch_variant<true, false, E>(*a, cfg, grid, smem, st, tm);                            \
         break;
     switch (a->epi) {
         CMGAN_TC_LAUNCH(CMGAN_EPI_NONE)

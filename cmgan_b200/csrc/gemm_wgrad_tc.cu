@@ -316,12 +316,18 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     while (tmem_cols < (ones_mma ? 2 * NB : NB)) tmem_cols <<= 1;
     const int ktiles = (a->Cin + MO - 1) / MO;
     const int ytiles = ktiles * a->ntaps;
-    // rows per CTA: enough CTAs for ~3 waves of 296 resident CTAs, at least 16 stages per CTA to amortise the TMEM round trip
-    long want = 888 / ytiles;
+    // rows per CTA: one full wave of 2 co-resident CTAs per SM (every CTA ends with one red.global pass over its dW tile, so more,
+    // smaller CTAs only add atomics and a ragged second wave), at least 8 stages per CTA
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    long want = (2L * sms) / ytiles;
     if (want < 1) want = 1;
     long mch = (a->M + want - 1) / want;
     mch = ((mch + RS - 1) / RS) * RS;
-    if (mch < 16 * RS) mch = 16 * RS;
+    if (mch < 8 * RS) mch = 8 * RS;
     dim3 grid((unsigned)((a->M + mch - 1) / mch), (unsigned)ytiles);
     const size_t smem = (size_t)stages * (A_STAGE + d_stage) + 4096 + 1024 + 8 * (2 * stages + 2) + 16;
     const bool aa = a->pro == CMGAN_PRO_NONE, da = a->prod == 0;

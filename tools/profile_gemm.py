@@ -11,7 +11,7 @@ from cmgan_b200 import ops  # noqa: E402
 from cmgan_b200.ops import call, gemm  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--which", default="ffn1", choices=["ffn1", "ffn1_dual", "ffn2", "conv4", "wgrad_ffn1", "wgrad_conv4", "plain256", "plain64"])
+ap.add_argument("--which", default="ffn1", choices=["ffn1", "ffn1_dual", "ffn2", "conv4", "wgrad_ffn1", "wgrad_conv4", "plain256", "plain64", "plain64k256"])
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
 ops.set_precision("tf32")
@@ -29,6 +29,10 @@ elif args.which in ("plain256", "plain64"):
     x, W, b = torch.randn(M, 64, device=dev), torch.randn(N, 64, device=dev), torch.randn(N, device=dev)
     out = torch.empty(M, N, device=dev)
     fn = lambda: gemm(A=x, lda=64, W=W, sb_k=1, sb_n=64, bias=b, C=out, ldc=N, M=M, N=N, Cin=64)
+elif args.which == "plain64k256":
+    x, W, b = torch.randn(M, 256, device=dev), torch.randn(64, 256, device=dev), torch.randn(64, device=dev)
+    out = torch.empty(M, 64, device=dev)
+    fn = lambda: gemm(A=x, lda=256, W=W, sb_k=1, sb_n=256, bias=b, C=out, ldc=64, M=M, N=64, Cin=256)
 elif args.which == "ffn1_dual":
     x, W, b = torch.randn(M, 64, device=dev), torch.randn(256, 64, device=dev), torch.randn(256, device=dev)
     h, a = torch.empty(M, 256, device=dev), torch.empty(M, 256, device=dev)
