@@ -12,6 +12,8 @@
 // instead, so that accumulator row holds sum_m D[m, n] = dbias.  Otherwise (Cin % 128 == 0, N <= 128) the CTAs of the first k tile issue
 // a second MMA per row group against a constant all-ones A operand into N extra TMEM columns (every row = dbias).  Only N = 256
 // with Cin % 128 == 0 (not on the hot path) still takes the separate colsum_kernel pass.
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched from the driver at run time)
+
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "gemm_device.cuh"
@@ -253,6 +255,164 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
     }
 }
 
+
+// ---- dense operands (no gather, no prologue, plain D): both operands by TMA.  A box = 32 rows x 32 floats lands as one
+// (row, 128 B) block of the MN-major SWIZZLE_128B_BASE32B layout (tensor-map swizzle 128B_ATOM_32B), so a stage is 4 boxes of A
+// (k blocks) + N/32 boxes of D, issued by one thread with the whole ring in flight (cp.async tops out near a third of HBM rate
+// per SM).  k blocks past Cin are never loaded: they are initialised once (zeros, or ones in row k = Cin for the bias gradient).
+// Warps 0-3 epilogue, warp 4 TMA producer, warp 5 TMEM allocation + MMA issue.
+constexpr int NT_TMA = 192;
+__global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_constant__ CmganGemmArgs g, int NB, int mch, int stages,
+                                                                   int tmem_cols, const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmD) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int d_stage = RS * NB * 4;
+    const uint32_t sA = base;
+    const uint32_t sD = base + stages * A_STAGE;
+    const uint32_t sOnes = sD + stages * d_stage;
+    const uint32_t bars = sOnes + 4096;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (stages + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * stages);
+    const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = blockIdx.y * MO;
+    const int kblk = min(4, (g.Cin - k0) / 32);              // valid 32-wide k blocks of this tile (Cin % 32 == 0)
+    const long mbeg = (long)blockIdx.x * mch;
+    const long mend = mbeg + mch < g.M ? mbeg + mch : g.M;
+    const int nst = (int)((mend - mbeg + RS - 1) / RS);
+    const bool spare_row = g.dbias != nullptr && kblk < 4;   // accumulator row k = Cin collects sum_m D[m, :]
+    const bool ones_mma = g.dbias != nullptr && g.Cin % MO == 0 && 2 * NB <= tmem_cols && blockIdx.y == 0;
+
+    // k blocks never touched by TMA: zeros, except (bias gradient) 1.0 at k = Cin for every row of the stage
+    for (int i = tid; i < stages * (4 - kblk) * 1024; i += NT_TMA) {
+        const int s = i / ((4 - kblk) * 1024), rem = i % ((4 - kblk) * 1024);
+        const int blk = kblk + rem / 1024, w = rem % 1024;       // w = float index inside the 4 KB block: row = w / 32
+        const int row = w >> 5, pos = w & 31;
+        const float v = (spare_row && blk == kblk && pos == ((row & 3) << 3)) ? 1.0f : 0.0f;     // element k = Cin sits in granule 0 ^ (row & 3)
+        reinterpret_cast<float*>(base_ptr + (sA - base) + (size_t)s * A_STAGE + (size_t)blk * BLK)[w] = v;
+    }
+    if (ones_mma)
+        for (int i = tid; i < 1024; i += NT_TMA) reinterpret_cast<float*>(base_ptr + (sOnes - base))[i] = 1.0f;
+    fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_ptr_addr, (uint32_t)tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(kblk + NB / 32) * BLK;
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                const int mrow = (int)(mbeg + (long)it * RS);
+                mbar_wait(empty_bar(s), par ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), tx);
+                for (int b = 0; b < kblk; ++b) tma_load_2d(sA + s * A_STAGE + b * BLK, &tmA, k0 + b * 32, mrow, full_bar(s));
+                for (int b = 0; b < NB / 32; ++b) tma_load_2d(sD + s * d_stage + b * BLK, &tmD, b * 32, mrow, full_bar(s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(MO, NB, 1, 1);
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % stages;
+                const uint32_t par = (uint32_t)((it / stages) & 1);
+                mbar_wait(full_bar(s), par);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < RS / 8; ++kb) {
+                    const uint64_t adesc = make_desc_sw128(sA + s * A_STAGE + kb * 1024, BLK, 512, 1);
+                    const uint64_t ddesc = make_desc_sw128(sD + s * d_stage + kb * 1024, BLK, 512, 1);
+                    umma_tf32(tmem_base, adesc, ddesc, idesc, (it | kb) != 0 ? 1u : 0u);
+                    if (ones_mma)
+                        umma_tf32(tmem_base + (uint32_t)NB, make_desc_sw128(sOnes, 1024, 512, 1), ddesc, idesc, (it | kb) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: dW tile += accumulator (one TMEM lane quarter per warp) ----------------
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int k = k0 + warp * 32 + lane;
+        const bool bias_row = spare_row && k == g.Cin;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int n0 = 0; n0 < NB; n0 += 16) {
+            float acc[16];
+            tmem_ld16(trow + (uint32_t)n0, acc);
+            if (bias_row) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
+            }
+            if (k < g.Cin) {
+                float* dst = g.C + (long)k * g.sb_k;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < g.N) atomicAdd(dst + (long)(n0 + j) * g.sb_n, acc[j]);
+            }
+        }
+        if (ones_mma && warp == 0) {
+            for (int n0 = 0; n0 < NB; n0 += 16) {
+                float acc[16];
+                tmem_ld16(trow + (uint32_t)(NB + n0), acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    }
+}
+
+using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encoder() {
+    static PFN_encodeTiled encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    return encode;
+}
+// rows x cols fp32 matrix with leading dimension ld, boxes of 32 x 32, MN-major SWIZZLE_128B_BASE32B image in shared memory
+bool make_map32(CUtensorMap* tm, const float* ptr, long long cols, long long rows, long long ld) {
+    PFN_encodeTiled enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // dbias[n] += sum_m prod(D[m, n])
 __global__ void colsum_kernel(const float* __restrict__ D, long ldd, long M, int N, int prod, float alpha, unsigned long long seed, unsigned thr,
                               float inv_keep, int rows_per_block, float* __restrict__ out, const unsigned long long* __restrict__ seed_dev) {
@@ -332,6 +492,18 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     const size_t smem = (size_t)stages * (A_STAGE + d_stage) + 4096 + 1024 + 8 * (2 * stages + 2) + 16;
     const bool aa = a->pro == CMGAN_PRO_NONE, da = a->prod == 0;
     int rc;
+    alignas(64) CUtensorMap tmA, tmD;
+    if (aa && da && !a->conv && a->ntaps == 1 && a->Cin % 32 == 0 &&
+        make_map32(&tmA, a->A + a->tap_off[0], a->Cin, a->M, a->lda) && make_map32(&tmD, a->D, a->N, a->M, a->ldd)) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+            if (e != cudaSuccess) { cmgan_set_error("gemm_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+            attr_set = true;
+        }
+        gemm_wgrad_tma_kernel<<<grid, NT_TMA, smem, st>>>(*a, NB, (int)mch, stages, tmem_cols, tmA, tmD);
+        rc = cmgan_check_launch("gemm_wgrad_tma_kernel");
+    } else
     if (aa && da) rc = launch<true, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     else if (aa) rc = launch<true, false>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
     else if (da) rc = launch<false, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
