@@ -90,24 +90,40 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __rest
                 reinterpret_cast<float4*>(DZ)[idx] = v;
             }
             __syncthreads();
-#pragma unroll 2
-            for (int tl = half * 16; tl < half * 16 + 16; ++tl) {
-                const int tok = t0 + tl;
-                if (tok >= sg.L) break;
-                // du[tok] = sum_k w[k] * dz[tok - k + 15]  ->  local rows tl + 30 - k
-                float du = 0.f;
+            // 4 consecutive tokens per pass share one sweep over the 34 staged rows they touch (68 shared-memory reads for 248 FMAs)
+#pragma unroll 1
+            for (int grp = 0; grp < 4; ++grp) {
+                const int tl = half * 16 + grp * 4;
+                if (t0 + tl >= sg.L) break;
+                float du[4] = {0.f, 0.f, 0.f, 0.f}, dzc[4];
 #pragma unroll
-                for (int k = 0; k < KS; ++k) du = fmaf(wr[k], DZ[(tl + 30 - k) * CH + c], du);
-                // dw[k] += dz[tok] * u[tok + k - 15] -> local rows tl + k
-                const float dzc = DZ[(tl + PADL) * CH + c];
+                for (int i = 0; i < 4; ++i) { dzc[i] = DZ[(tl + i + PADL) * CH + c]; db += dzc[i]; }
+                // du[tok] = sum_k w[k] * dz[tok - k + 15]: staged row tl + m feeds token i with k = 30 - m + i
 #pragma unroll
-                for (int k = 0; k < KS; ++k) dwr[k] = fmaf(dzc, U[(tl + k) * CH + c], dwr[k]);
-                db += dzc;
-                const long row = base + (long)tok * sg.tok_stride;
-                const float sg_ = SG[tl * CH + c];
-                const float u = U[(tl + PADL) * CH + c];            // a * sigmoid(b)
-                dg[row * (2 * CH) + c] = du * sg_;
-                dg[row * (2 * CH) + CH + c] = du * u * (1.f - sg_);
+                for (int m = 0; m < KS + 3; ++m) {
+                    const float z = DZ[(tl + m) * CH + c];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (m - i >= 0 && m - i < KS) du[i] = fmaf(wr[KS - 1 - m + i], z, du[i]);
+                }
+                // dw[k] += dz[tok] * u[tok + k - 15]: staged row tl + m feeds (token i, k = m - i)
+#pragma unroll
+                for (int m = 0; m < KS + 3; ++m) {
+                    const float u = U[(tl + m) * CH + c];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (m - i >= 0 && m - i < KS) dwr[m - i] = fmaf(dzc[i], u, dwr[m - i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int tok = t0 + tl + i;
+                    if (tok >= sg.L) break;
+                    const long row = base + (long)tok * sg.tok_stride;
+                    const float sg_ = SG[(tl + i) * CH + c];
+                    const float u = U[(tl + i + PADL) * CH + c];            // a * sigmoid(b)
+                    dg[row * (2 * CH) + c] = du[i] * sg_;
+                    dg[row * (2 * CH) + CH + c] = du[i] * u * (1.f - sg_);
+                }
             }
         }
     }

@@ -126,6 +126,35 @@ __global__ void norm_stats_kernel(const float* __restrict__ x, long ldx, long ro
     }
 }
 
+// same, 128-bit loads: thread = (row-subgroup, 4 channels); C, ldx multiples of 4, x 16-byte aligned
+__global__ void norm_stats4_kernel(const float* __restrict__ x, long ldx, long rows_per_group, int C, int chunk, double* __restrict__ sums) {
+    __shared__ float sm[256][8];
+    const int grp = blockIdx.y, cv = C / 4;
+    const long r_beg = (long)blockIdx.x * chunk;
+    const long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
+    const int c4 = threadIdx.x % cv, rg = threadIdx.x / cv, nrg = blockDim.x / cv;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    const float* base = x + ((long)grp * rows_per_group) * ldx + c4 * 4;
+    if (rg < nrg) {
+#pragma unroll 4
+        for (long r = r_beg + rg; r < r_end; r += nrg) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * ldx));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+        }
+    }
+    float* o = sm[threadIdx.x];
+    o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; o[4] = q.x; o[5] = q.y; o[6] = q.z; o[7] = q.w;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x, cc = c >> 2, j = c & 3;
+        double ds = 0.0, dq = 0.0;
+        for (int g = 0; g < nrg; ++g) { ds += sm[g * cv + cc][j]; dq += sm[g * cv + cc][4 + j]; }
+        atomicAdd(sums + ((long)grp * C + c) * 2, ds);
+        atomicAdd(sums + ((long)grp * C + c) * 2 + 1, dq);
+    }
+}
+
 // mode 0: InstanceNorm / train-mode BatchNorm: statistics from sums (biased variance for the normalisation)
 // mode 1: eval-mode BatchNorm: running statistics
 // outputs per (grp, c): scale = gamma*rstd, shift = beta - mean*scale, mean, rstd (table stride = tstride)
@@ -227,25 +256,43 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, con
 }
 
 // y[row, c] = act(x*scale+shift) materialised (used where the consumer is not a GEMM with a prologue)
-__global__ void norm_apply_kernel(const float* __restrict__ x, long ldx, long rows_per_group, int G, int C, int act,
-                                  const float* __restrict__ scale, const float* __restrict__ shift, long tstride,
-                                  const float* __restrict__ slope, float* __restrict__ y, long ldy) {
-    long total = (long)G * rows_per_group * C;
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int c = (int)(i % C);
-    long row = i / C;
-    long t = (row / rows_per_group) * tstride + c;
-    float z = __ldg(x + row * ldx + c) * scale[t] + shift[t];
-    const int a = act & 15;
-    if (a == 1 && z < 0.f) z *= slope[c];
+__device__ __forceinline__ float norm_act1(float z, int a, float sl, bool round_tf32) {
+    if (a == 1 && z < 0.f) z *= sl;
     else if (a == 2) z = swishf_(z);
-    if (act & 16) {        // consumer is a tf32 tensor-core GEMM fed by cp.async: round (not truncate) once, here
+    if (round_tf32) {      // consumer is a tf32 tensor-core GEMM fed by cp.async / TMA: round (not truncate) once, here
         uint32_t r;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(z));
         z = __uint_as_float(r);
     }
-    y[row * ldy + c] = z;
+    return z;
+}
+// VEC = 4: C, ldx, ldy, tstride multiples of 4 and 16-byte aligned pointers (every call of the hot path); VEC = 1: general
+template <int VEC>
+__global__ void norm_apply_kernel(const float* __restrict__ x, long ldx, long rows_per_group, int G, int C, int act,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, long tstride,
+                                  const float* __restrict__ slope, float* __restrict__ y, long ldy) {
+    const int cv = C / VEC;
+    long total = (long)G * rows_per_group * cv;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % cv) * VEC;
+    long row = i / cv;
+    long t = (row / rows_per_group) * tstride + c;
+    const int a = act & 15;
+    const bool rnd = (act & 16) != 0;
+    if (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ldx + c));
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + t)), sh = __ldg(reinterpret_cast<const float4*>(shift + t));
+        float4 sl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a == 1) sl = __ldg(reinterpret_cast<const float4*>(slope + c));
+        float4 o;
+        o.x = norm_act1(fmaf(v.x, sc.x, sh.x), a, sl.x, rnd); o.y = norm_act1(fmaf(v.y, sc.y, sh.y), a, sl.y, rnd);
+        o.z = norm_act1(fmaf(v.z, sc.z, sh.z), a, sl.z, rnd); o.w = norm_act1(fmaf(v.w, sc.w, sh.w), a, sl.w, rnd);
+        *reinterpret_cast<float4*>(y + row * ldy + c) = o;
+    } else {
+        float z = fmaf(__ldg(x + row * ldx + c), scale[t], shift[t]);
+        y[row * ldy + c] = norm_act1(z, a, a == 1 ? slope[c] : 0.f, rnd);
+    }
 }
 
 __global__ void fill_kernel(float* p, long n, float v) {
@@ -327,6 +374,13 @@ static int norm_threads(int C) { return C <= 256 ? 256 : C; }
 CMGAN_API int cmgan_norm_stats(const float* x, long long ldx, int G, long long rows_per_group, int C, double* sums, void* stream) {
     CMGAN_REQUIRE(x && sums && C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_stats: C=%d unsupported", C);
     if (G == 0 || rows_per_group == 0) return 0;
+    if (C % 4 == 0 && ldx % 4 == 0 && (((uintptr_t)x) & 15) == 0) {
+        const int nrg4 = 256 / (C / 4);
+        const int chunk4 = nrg4 * 16;                 // 16 x 128-bit loads per thread; ~1000 blocks on the hot shapes
+        dim3 grid4(cdiv(rows_per_group, chunk4), G);
+        norm_stats4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(x, ldx, rows_per_group, C, chunk4, sums);
+        return cmgan_check_launch("norm_stats4_kernel");
+    }
     int nrg = 256 / C;
     int chunk = nrg * 64;
     dim3 grid(cdiv(rows_per_group, chunk), G);
@@ -380,7 +434,10 @@ CMGAN_API int cmgan_norm_apply(const float* x, long long ldx, int G, long long r
     CMGAN_REQUIRE(x && y && scale && shift, "cmgan_norm_apply: null pointer");
     long total = (long)G * rows_per_group * C;
     if (total == 0) return 0;
-    norm_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows_per_group, G, C, act, scale, shift, tstride, slope, y, ldy);
+    const bool vec = C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && tstride % 4 == 0 &&
+                     ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)scale) | ((uintptr_t)shift) | ((uintptr_t)slope)) & 15) == 0;
+    if (vec) norm_apply_kernel<4><<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows_per_group, G, C, act, scale, shift, tstride, slope, y, ldy);
+    else norm_apply_kernel<1><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows_per_group, G, C, act, scale, shift, tstride, slope, y, ldy);
     return cmgan_check_launch("norm_apply_kernel");
 }
 
