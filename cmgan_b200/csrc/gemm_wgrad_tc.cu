@@ -256,14 +256,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_wgrad_tc_kernel(const __grid
 }
 
 
-// ---- dense operands (no gather, no prologue, plain D): both operands by TMA.  A box = 32 rows x 32 floats lands as one
-// (row, 128 B) block of the MN-major SWIZZLE_128B_BASE32B layout (tensor-map swizzle 128B_ATOM_32B), so a stage is 4 boxes of A
-// (k blocks) + N/32 boxes of D, issued by one thread with the whole ring in flight (cp.async tops out near a third of HBM rate
-// per SM).  k blocks past Cin are never loaded: they are initialised once (zeros, or ones in row k = Cin for the bias gradient).
+// ---- plain operands (no prologue, plain D; dense rows or a same-size convolution gather): both operands by TMA.
+// A box = 32 rows x 32 floats lands as one (row, 128 B) block of the MN-major SWIZZLE_128B_BASE32B layout (tensor-map swizzle
+// 128B_ATOM_32B), so a stage is 4 boxes of A (k blocks) + N/32 boxes of D, issued by one thread with the whole ring in flight
+// (cp.async tops out near a third of HBM rate per SM).  The activation is described as a (C, W, H, B) tensor and a stage is 32
+// consecutive positions of one image line: the tap's (dy, dx) is added to the box coordinates and the unit zero-fills whatever
+// falls outside the image (the convolution's padding) or past the line end; a dense matrix is the one-line case (W = M).
+// k blocks past Cin are never loaded: they are initialised once (zeros, or ones in row k = Cin for the bias gradient).
 // Warps 0-3 epilogue, warp 4 TMA producer, warp 5 TMEM allocation + MMA issue.
 constexpr int NT_TMA = 192;
-__global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_constant__ CmganGemmArgs g, int NB, int mch, int stages,
-                                                                   int tmem_cols, const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_constant__ CmganGemmArgs g, int NB, int ipc, int stages,
+                                                                   int tmem_cols, int items, int fblocks, int lines_h,
+                                                                   const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmD) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -279,12 +283,12 @@ __global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_
     const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int k0 = blockIdx.y * MO;
+    const int ktiles = (g.Cin + MO - 1) / MO;
+    const int tap = blockIdx.y / ktiles, k0 = (blockIdx.y % ktiles) * MO;
     const int kblk = min(4, (g.Cin - k0) / 32);              // valid 32-wide k blocks of this tile (Cin % 32 == 0)
-    const long mbeg = (long)blockIdx.x * mch;
-    const long mend = mbeg + mch < g.M ? mbeg + mch : g.M;
-    const int nst = (int)((mend - mbeg + RS - 1) / RS);
-    const bool spare_row = g.dbias != nullptr && kblk < 4;   // accumulator row k = Cin collects sum_m D[m, :]
+    const int ibeg = blockIdx.x * ipc;                       // items = (image line, block of 32 positions)
+    const int nst = min(ipc, items - ibeg);
+    const bool spare_row = g.dbias != nullptr && kblk < 4 && tap == 0;   // accumulator row k = Cin collects sum_m D[m, :]
     const bool ones_mma = g.dbias != nullptr && g.Cin % MO == 0 && 2 * NB <= tmem_cols && blockIdx.y == 0;
 
     // k blocks never touched by TMA: zeros, except (bias gradient) 1.0 at k = Cin for every row of the stage
@@ -313,14 +317,17 @@ __global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_
     if (warp == 4) {
         if (lane == 0) {
             const uint32_t tx = (uint32_t)(kblk + NB / 32) * BLK;
+            const int dy = g.conv ? g.dy[tap] : 0, dx = g.conv ? g.dx[tap] : 0;
             for (int it = 0; it < nst; ++it) {
                 const int s = it % stages;
                 const uint32_t par = (uint32_t)((it / stages) & 1);
-                const int mrow = (int)(mbeg + (long)it * RS);
+                const int item = ibeg + it;
+                const int line = item / fblocks, x0 = (item - line * fblocks) * RS;
+                const int bimg = line / lines_h, y = line - bimg * lines_h;
                 mbar_wait(empty_bar(s), par ^ 1u);
                 mbar_arrive_expect_tx(full_bar(s), tx);
-                for (int b = 0; b < kblk; ++b) tma_load_2d(sA + s * A_STAGE + b * BLK, &tmA, k0 + b * 32, mrow, full_bar(s));
-                for (int b = 0; b < NB / 32; ++b) tma_load_2d(sD + s * d_stage + b * BLK, &tmD, b * 32, mrow, full_bar(s));
+                for (int b = 0; b < kblk; ++b) tma_load_4d(sA + s * A_STAGE + b * BLK, &tmA, k0 + b * 32, x0 + dx, y + dy, bimg, full_bar(s));
+                for (int b = 0; b < NB / 32; ++b) tma_load_3d(sD + s * d_stage + b * BLK, &tmD, b * 32, x0, line, full_bar(s));
             }
         }
         __syncwarp();
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_
                     if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
             }
             if (k < g.Cin) {
-                float* dst = g.C + (long)k * g.sb_k;
+                float* dst = g.C + (long)tap * g.sb_tap + (long)k * g.sb_k;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (n0 + j < g.N) atomicAdd(dst + (long)(n0 + j) * g.sb_n, acc[j]);
@@ -401,15 +408,16 @@ PFN_encodeTiled get_encoder() {
     }
     return encode;
 }
-// rows x cols fp32 matrix with leading dimension ld, boxes of 32 x 32, MN-major SWIZZLE_128B_BASE32B image in shared memory
-bool make_map32(CUtensorMap* tm, const float* ptr, long long cols, long long rows, long long ld) {
+// fp32 rows of `cols` floats (leading dimension ld) indexed (x < W, y < H, b < B) [rank 4] or (x < W, line < H) [rank 3]; boxes of
+// 32 floats x 32 positions of one line; MN-major SWIZZLE_128B_BASE32B image in shared memory
+bool make_map32(CUtensorMap* tm, int rank, const float* ptr, long long cols, long long W, long long H, long long B, long long ld) {
     PFN_encodeTiled enc = get_encoder();
     if (!enc) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {32, 32};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstride[3] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)W * ld * sizeof(float), (cuuint64_t)H * W * ld * sizeof(float)};
+    const cuuint32_t box[4] = {32, 32, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -493,15 +501,26 @@ int cmgan_gemm_wgrad_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     const bool aa = a->pro == CMGAN_PRO_NONE, da = a->prod == 0;
     int rc;
     alignas(64) CUtensorMap tmA, tmD;
-    if (aa && da && !a->conv && a->ntaps == 1 && a->Cin % 32 == 0 &&
-        make_map32(&tmA, a->A + a->tap_off[0], a->Cin, a->M, a->lda) && make_map32(&tmD, a->D, a->N, a->M, a->ldd)) {
+    // TMA path: dense rows, or a convolution whose output grid equals its input grid (taps = coordinate offsets, padding = OOB fill)
+    bool same_off = true;
+    for (int t = 1; t < a->ntaps; ++t) same_off = same_off && a->tap_off[t] == a->tap_off[0];
+    const bool dense = !a->conv && a->ntaps == 1;
+    const bool conv_same = a->conv && a->mul_y == 1 && a->mul_x == 1 && a->div_y == 1 && a->div_x == 1 && a->OH == a->IH && a->OW == a->IW &&
+                           same_off && a->M % ((long long)a->OH * a->OW) == 0;
+    const long long W = dense ? a->M : a->OW, Hh = dense ? 1 : a->OH, Bn = dense ? 1 : a->M / ((long long)a->OH * a->OW);
+    const long long fblocks = (W + RS - 1) / RS, items = Hh * Bn * fblocks;
+    if (aa && da && (dense || conv_same) && a->Cin % 32 == 0 && items < (1ll << 30) &&
+        make_map32(&tmA, 4, a->A + a->tap_off[0], a->Cin, W, Hh, Bn, a->lda) && make_map32(&tmD, 3, a->D, a->N, W, Hh * Bn, 1, a->ldd)) {
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
             if (e != cudaSuccess) { cmgan_set_error("gemm_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
             attr_set = true;
         }
-        gemm_wgrad_tma_kernel<<<grid, NT_TMA, smem, st>>>(*a, NB, (int)mch, stages, tmem_cols, tmA, tmD);
+        long long ipc = (items + want - 1) / want;       // items per CTA: one full wave
+        if (ipc < 8) ipc = 8;
+        dim3 grid_t((unsigned)((items + ipc - 1) / ipc), (unsigned)ytiles);
+        gemm_wgrad_tma_kernel<<<grid_t, NT_TMA, smem, st>>>(*a, NB, (int)ipc, stages, tmem_cols, (int)items, (int)fblocks, (int)Hh, tmA, tmD);
         rc = cmgan_check_launch("gemm_wgrad_tma_kernel");
     } else
     if (aa && da) rc = launch<true, true>(a, grid, smem, NB, (int)mch, stages, tmem_cols, st);
