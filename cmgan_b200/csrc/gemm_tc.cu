@@ -58,7 +58,10 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
     out[(chunk * BN + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
 }
 
-struct TcCfg { int BN, stages, tmem_cols, resident, ntiles, tma; };
+// tma: 0 = cp.async / register producers, 1 = dense 2-D tensor map, 2 = same-size convolution: tiles are 16 x 8 (h x w) patches of one image
+// (pw = 8 positions along w, ph = 16 lines), fetched through a 4-D tensor map with the tap offset added to the coordinates
+struct TcCfg { int BN, stages, tmem_cols, resident, ntiles, tma, nfx, nty, W, H; };
+constexpr int PW = 8, PH = 16;
 
 template <bool ASYNC_A, bool EPI8, int EPI>
 __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI8) ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
@@ -119,7 +122,14 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                     const uint32_t par = (uint32_t)((q / stages) & 1);
                     mbar_wait(empty_bar(s), par ^ 1u);
                     mbar_arrive_expect_tx(full_bar(s), (uint32_t)A_STAGE_BYTES);
-                    tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, ch * KC, (blockIdx.x + lt * gridDim.x) * BM, full_bar(s));
+                    const int tile = blockIdx.x + lt * gridDim.x;
+                    if (cfg.tma == 1) {
+                        tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, ch * KC, tile * BM, full_bar(s));
+                    } else {        // patch (bimg, ty, fx): rows r = 8 * line + position; padding and ragged edges come back as zeros
+                        const int fx = tile % cfg.nfx, ty = (tile / cfg.nfx) % cfg.nty, bimg = tile / (cfg.nfx * cfg.nty);
+                        const int tap = ch / cpt, kc = ch - tap * cpt;
+                        tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, kc * KC, fx * PW + g.dx[tap], ty * PH + g.dy[tap], bimg, full_bar(s));
+                    }
                 }
             }
             __syncwarp();
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
         const uint32_t seed32 = DROPS ? cmgan_seed32(eff_seed(g)) : 0u;
         const uint32_t thr16 = g.drop_thr >> 16;
         const bool drop_on = DROPS && g.drop_thr != 0u;
+        const bool patch = cfg.tma == 2;
         const float inv_keep = g.inv_keep, alpha = g.alpha;
         // auxiliary operand read at the output position: R (DROP_RES, optional), aux (DSWISH_DROP / DBNSWISH), old C (ACC)
         const float* xbase = nullptr;
@@ -283,21 +294,34 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
         else if (EPI == CMGAN_EPI_ACC) { xbase = g.C; ldx = g.ldc; }
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int buf = lt & 1;
-            const int mrow0 = (blockIdx.x + lt * gridDim.x) * BM + q4 * 32;
-            const int rows_valid = g.M - mrow0;                 // rows of this quarter inside the matrix (may be <= 0 or >= 32)
-            const int npass = rsub < rows_valid ? min(16, (rows_valid - rsub + 1) >> 1) : 0;
-            const long mfirst = (long)mrow0 + rsub;
-            const long xstep = 2 * ldx;
+            // rows of this TMEM lane quarter.  Flat tiles: 32 consecutive rows.  Patch tiles (cfg.tma == 2): 4 image lines x 8 positions.
+            // Pass ps handles quarter rows 2 ps + rsub; its row index is mfirst + (ps >> 2) * hi_rows + 2 * (ps & 3).
+            const int tile = blockIdx.x + lt * gridDim.x;
+            long mfirst;
+            int hi_rows, vhi, vlo;          // valid: flat: 8 (ps >> 2) + 2 (ps & 3) + rsub < vlo;  patch: (ps >> 2) < vhi && 2 (ps & 3) + rsub < vlo
+            if (patch) {
+                const int fx = tile % cfg.nfx, ty = (tile / cfg.nfx) % cfg.nty, bimg = tile / (cfg.nfx * cfg.nty);
+                const int y0 = ty * PH + q4 * 4, x0 = fx * PW;
+                mfirst = ((long)bimg * cfg.H + y0) * cfg.W + x0 + rsub;
+                hi_rows = cfg.W; vhi = cfg.H - y0; vlo = cfg.W - x0;
+            } else {
+                const int mrow0 = tile * BM + q4 * 32;
+                mfirst = (long)mrow0 + rsub;
+                hi_rows = 8; vhi = 4; vlo = g.M - mrow0;
+            }
+            auto row_ok = [&](int ps) { return patch ? ((ps >> 2) < vhi && 2 * (ps & 3) + rsub < vlo) : (2 * ps + rsub < vlo); };
+            auto row_delta = [&](int ps) { return (long)(ps >> 2) * hi_rows + 2 * (ps & 3); };
+            const bool any_row = row_ok(0);
             // the auxiliary operand does not depend on the accumulator: its first loads are issued before waiting for the MMAs,
             // later batches (4 passes = 8 rows each) one batch ahead of their use
             float4 ex[RING][4];                                 // slot = batch index % RING; PD batches of loads in flight
             auto prefetch = [&](int sl, int b4, float4* dst) {
                 const int n = sl * SLAB + col4;
                 if (xbase == nullptr || n >= BN) return;
-                const float* xp = xbase + mfirst * ldx + n + (long)(b4 * 4) * xstep;
+                const float* xp = xbase + mfirst * ldx + n;
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (b4 * 4 + u < npass) dst[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
+                    if (row_ok(b4 * 4 + u)) dst[u] = __ldg(reinterpret_cast<const float4*>(xp + row_delta(b4 * 4 + u) * ldx));
             };
             if (half < nslabs) { prefetch(half, 0, ex[0]); if (PD == 2) prefetch(half, 1, ex[1]); }
             mbar_wait(tfull_bar + 8u * buf, (uint32_t)((lt >> 1) & 1));
@@ -330,7 +354,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                     released = true;
                 }
                 __syncwarp();
-                if (col4 < ncols && npass > 0) {
+                if (col4 < ncols && any_row) {
                     const int n = n0 + col4;
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), e0v = bias4, e1v = bias4;
                     if (g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
@@ -338,9 +362,9 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                     float* cptr = g.C ? g.C + mfirst * g.ldc + n : nullptr;
                     float* c2ptr = EPI == CMGAN_EPI_SWISH_DUAL ? g.C2 + mfirst * g.ldc2 + n : nullptr;
                     const float* sptr = stg + rsub * STG_LD + col4;
-                    const long cstep = 2 * (long)g.ldc, c2step = 2 * (long)g.ldc2;
+                    const long ldc = g.ldc, ldc2 = g.ldc2;
                     const uint32_t pair = (uint32_t)(((unsigned long long)mfirst * (unsigned long long)g.N + (unsigned long long)n) >> 1);
-                    const uint32_t pstep = (uint32_t)g.N;       // two rows further = N pairs further
+                    const uint32_t phalf = (uint32_t)g.N >> 1;       // one row further = N / 2 pairs further
 #pragma unroll
                     for (int b4 = 0; b4 < 4; ++b4) {
                         if (b4 + PD < 4) prefetch(sl, b4 + PD, ex[(b4 + PD) % RING]);
@@ -348,12 +372,13 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int ps = b4 * 4 + u;
-                            if (ps >= npass) break;
+                            if (!row_ok(ps)) continue;
+                            const long rd = row_delta(ps);
                             const float4 a = *reinterpret_cast<const float4*>(sptr + ps * 2 * STG_LD);
                             float v[4] = {a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w};
                             float ds[4] = {1.f, 1.f, 1.f, 1.f};
                             if (DROPS && drop_on) {
-                                const uint32_t pr = pair + (uint32_t)ps * pstep;
+                                const uint32_t pr = pair + (uint32_t)rd * phalf;
                                 const uint32_t h0 = cmgan_mix32((pr * 0x9E3779B1u) ^ seed32), h1 = cmgan_mix32(((pr + 1u) * 0x9E3779B1u) ^ seed32);
                                 ds[0] = (h0 & 0xFFFFu) >= thr16 ? inv_keep : 0.f; ds[1] = (h0 >> 16) >= thr16 ? inv_keep : 0.f;
                                 ds[2] = (h1 & 0xFFFFu) >= thr16 ? inv_keep : 0.f; ds[3] = (h1 >> 16) >= thr16 ? inv_keep : 0.f;
@@ -361,10 +386,10 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                             const float4 xe = ex[b4 % RING][u];
                             const float x[4] = {xe.x, xe.y, xe.z, xe.w};
                             if (EPI == CMGAN_EPI_SWISH_DUAL) {
-                                if (cptr) *reinterpret_cast<float4*>(cptr + ps * cstep) = make_float4(v[0], v[1], v[2], v[3]);
+                                if (cptr) *reinterpret_cast<float4*>(cptr + rd * ldc) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) v[j] = swishf_(v[j]) * ds[j];
-                                *reinterpret_cast<float4*>(c2ptr + ps * c2step) = make_float4(v[0], v[1], v[2], v[3]);
+                                *reinterpret_cast<float4*>(c2ptr + rd * ldc2) = make_float4(v[0], v[1], v[2], v[3]);
                                 continue;
                             }
                             if (EPI == CMGAN_EPI_DROP_RES) {
@@ -381,7 +406,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) v[j] = alpha * v[j] + x[j];
                             }
-                            *reinterpret_cast<float4*>(cptr + ps * cstep) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(cptr + rd * ldc) = make_float4(v[0], v[1], v[2], v[3]);
                         }
                     }
                 } else if (sl + NH < nslabs) {
@@ -425,6 +450,18 @@ int g_num_sms = 0;
 
 using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encoder() {
+    static PFN_encodeTiled encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    return encode;
+}
 
 template <bool ASYNC_A, bool EPI8, int EPI>
 int launch_variant(const CmganGemmArgs& a, const TcCfg& cfg, int grid, size_t smem, cudaStream_t st, const CUtensorMap& tm) {
@@ -472,16 +509,9 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     cfg.tma = 0;
+    cfg.nfx = cfg.nty = 1; cfg.W = cfg.H = 0;
     if (a->pro == CMGAN_PRO_NONE && !a->conv && a->ntaps == 1 && a->lda % 4 == 0) {
-        static PFN_encodeTiled encode = nullptr;
-        static bool tried = false;
-        if (!tried) {
-            tried = true;
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-                encode = reinterpret_cast<PFN_encodeTiled>(fn);
-        }
+        PFN_encodeTiled encode = get_encoder();
         if (encode) {
             const cuuint64_t gdim[2] = {(cuuint64_t)a->Cin, (cuuint64_t)a->M};
             const cuuint64_t gstride[1] = {(cuuint64_t)a->lda * sizeof(float)};
@@ -491,6 +521,29 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r == CUDA_SUCCESS) cfg.tma = 1;
+        }
+    }
+    // same-size convolution (taps = coordinate offsets of a (C, W, H, B) tensor, padding = out-of-bounds zero fill): 16 x 8 patch tiles
+    bool same_off = true;
+    for (int t = 1; t < a->ntaps; ++t) same_off = same_off && a->tap_off[t] == a->tap_off[0];
+    if (a->pro == CMGAN_PRO_NONE && a->conv && a->mul_y == 1 && a->mul_x == 1 && a->div_y == 1 && a->div_x == 1 && a->OH == a->IH &&
+        a->OW == a->IW && same_off && a->M % ((long long)a->OH * a->OW) == 0) {
+        PFN_encodeTiled encode = get_encoder();
+        if (encode) {
+            const long long Bn = a->M / ((long long)a->OH * a->OW);
+            const cuuint64_t gdim[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->IW, (cuuint64_t)a->IH, (cuuint64_t)Bn};
+            const cuuint64_t gstride[3] = {(cuuint64_t)a->lda * sizeof(float), (cuuint64_t)a->IW * a->lda * sizeof(float),
+                                           (cuuint64_t)a->IH * a->IW * a->lda * sizeof(float)};
+            const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)PW, (cuuint32_t)PH, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->A + a->tap_off[0]), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            const long long nfx = cdiv(a->OW, PW), nty = cdiv(a->OH, PH);
+            if (r == CUDA_SUCCESS && Bn * nfx * nty < (1ll << 30)) {
+                cfg.tma = 2; cfg.nfx = (int)nfx; cfg.nty = (int)nty; cfg.W = a->OW; cfg.H = a->OH;
+                cfg.ntiles = (int)(Bn * nfx * nty);
+            }
         }
     }
     long total = (long)nchunks * cfg.BN * KC;

@@ -117,7 +117,14 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
         e0.record()
         lib().call(name, ctypes.byref(a), stream())
         e1.record()
-        PROBE.append((name, M, N, Cin * ntaps, e0, e1))
+        # algorithmic bytes of the launch: A read once (not once per tap), C written, every auxiliary operand of the epilogue read once
+        # (residual / saved activation / accumulated C), the second output of the dual epilogue, the weights; wgrad: A and D read once
+        if wgrad:
+            nbytes = 4 * (M * Cin + M * N)
+        else:
+            extra = (1 if (R is not None or aux is not None or epi == EPI_ACC) else 0) + (1 if C2 is not None else 0)
+            nbytes = 4 * (M * Cin + M * N * (1 + extra) + N * Cin * ntaps)
+        PROBE.append((name, M, N, Cin * ntaps, e0, e1, nbytes))
     else:
         lib().call(name, ctypes.byref(a), stream())
     LAUNCHES += 2 if ws is not None else 1

@@ -7,13 +7,16 @@ import sys
 d = json.load(open(sys.argv[1]))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 agg = collections.defaultdict(lambda: [0, 0.0])
-for n, M, N, K, us in d:
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+for rec in d:
+    n, M, N, K, us = rec[:5]
+    nb = rec[5] if len(rec) > 5 else 4.0 * M * (N + K)
     key = (n.replace("cmgan_gemm_", "").replace("_f32", ""), M, N, K)
     agg[key][0] += 1
     agg[key][1] += us
+    agg[key][2] += nb
 tot = sum(v[1] for v in agg.values())
 print(f"total GEMM time {tot / 1e3:.2f} ms over {len(d)} calls")
-for (n, M, N, K), (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for (n, M, N, K), (c, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     fl = 2.0 * M * N * K * c
-    by = 4.0 * M * (N + K) * c if n == "rows" else 4.0 * M * (N + K) * c
-    print(f"{n:6s} M={M:7d} N={N:4d} K={K:5d} x{c:3d} {us:9.0f} us  {us / c:7.1f} us/call  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s (A+C once)")
+    print(f"{n:6s} M={M:7d} N={N:4d} K={K:5d} x{c:3d} {us:9.0f} us  {us / c:7.1f} us/call  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s (algorithmic)")
