@@ -63,7 +63,7 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
 struct TcCfg { int BN, stages, tmem_cols, resident, ntiles, tma, nfx, nty, W, H; };
 constexpr int PW = 8, PH = 16;
 
-template <bool ASYNC_A, bool EPI8, int EPI>
+template <bool ASYNC_A, bool EPI8, int EPI, bool PATCH>
 __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI8) ? 2 : 1) gemm_rows_tc_kernel(const __grid_constant__ CmganGemmArgs g, const float* __restrict__ Bp,
                                                                     const TcCfg cfg, const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ uint8_t smem_raw[];
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                     mbar_wait(empty_bar(s), par ^ 1u);
                     mbar_arrive_expect_tx(full_bar(s), (uint32_t)A_STAGE_BYTES);
                     const int tile = blockIdx.x + lt * gridDim.x;
-                    if (cfg.tma == 1) {
+                    if (!PATCH) {
                         tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, ch * KC, tile * BM, full_bar(s));
                     } else {        // patch (bimg, ty, fx): rows r = 8 * line + position; padding and ragged edges come back as zeros
                         const int fx = tile % cfg.nfx, ty = (tile / cfg.nfx) % cfg.nty, bimg = tile / (cfg.nfx * cfg.nty);
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
         const uint32_t seed32 = DROPS ? cmgan_seed32(eff_seed(g)) : 0u;
         const uint32_t thr16 = g.drop_thr >> 16;
         const bool drop_on = DROPS && g.drop_thr != 0u;
-        const bool patch = cfg.tma == 2;
+        constexpr bool patch = PATCH;          // compile-time: the flat-tile epilogue keeps its simple row arithmetic
         const float inv_keep = g.inv_keep, alpha = g.alpha;
         // auxiliary operand read at the output position: R (DROP_RES, optional), aux (DSWISH_DROP / DBNSWISH), old C (ACC)
         const float* xbase = nullptr;
@@ -463,15 +463,15 @@ PFN_encodeTiled get_encoder() {
     return encode;
 }
 
-template <bool ASYNC_A, bool EPI8, int EPI>
+template <bool ASYNC_A, bool EPI8, int EPI, bool PATCH = false>
 int launch_variant(const CmganGemmArgs& a, const TcCfg& cfg, int grid, size_t smem, cudaStream_t st, const CUtensorMap& tm) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) { cmgan_set_error("gemm_rows_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
         attr_set = true;
     }
-    gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI><<<grid, EPI8 ? NTHREADS8 : NTHREADS4, smem, st>>>(a, a.ws, cfg, tm);
+    gemm_rows_tc_kernel<ASYNC_A, EPI8, EPI, PATCH><<<grid, EPI8 ? NTHREADS8 : NTHREADS4, smem, st>>>(a, a.ws, cfg, tm);
     return 0;
 }
 
@@ -526,7 +526,7 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     // same-size convolution (taps = coordinate offsets of a (C, W, H, B) tensor, padding = out-of-bounds zero fill): 16 x 8 patch tiles
     bool same_off = true;
     for (int t = 1; t < a->ntaps; ++t) same_off = same_off && a->tap_off[t] == a->tap_off[0];
-    if (a->pro == CMGAN_PRO_NONE && a->conv && a->mul_y == 1 && a->mul_x == 1 && a->div_y == 1 && a->div_x == 1 && a->OH == a->IH &&
+    if (a->pro == CMGAN_PRO_NONE && (a->epi == CMGAN_EPI_NONE || a->epi == CMGAN_EPI_ACC) && a->conv && a->mul_y == 1 && a->mul_x == 1 && a->div_y == 1 && a->div_x == 1 && a->OH == a->IH &&
         a->OW == a->IW && same_off && a->M % ((long long)a->OH * a->OW) == 0) {
         PFN_encodeTiled encode = get_encoder();
         if (encode) {
@@ -558,6 +558,14 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
              : variant == 1 ? launch_variant<true, true, E>(*a, cfg, grid, smem, st, tm)                              \
                             : launch_variant<true, false, E>(*a, cfg, grid, smem, st, tm);                            \
         break;
+    if (cfg.tma == 2) {      // patch tiles (same-size convolutions): forward (plain) and data-gradient (accumulating) epilogues
+        if (a->epi == CMGAN_EPI_NONE)
+            rc = epi8 ? launch_variant<true, true, CMGAN_EPI_NONE, true>(*a, cfg, grid, smem, st, tm)
+                      : launch_variant<true, false, CMGAN_EPI_NONE, true>(*a, cfg, grid, smem, st, tm);
+        else
+            rc = epi8 ? launch_variant<true, true, CMGAN_EPI_ACC, true>(*a, cfg, grid, smem, st, tm)
+                      : launch_variant<true, false, CMGAN_EPI_ACC, true>(*a, cfg, grid, smem, st, tm);
+    } else
     switch (a->epi) {
         CMGAN_TC_LAUNCH(CMGAN_EPI_NONE)
         CMGAN_TC_LAUNCH(CMGAN_EPI_DROP_RES)
