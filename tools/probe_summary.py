@@ -11,10 +11,11 @@ agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for rec in d:
     n, M, N, K, us = rec[:5]
     nb = rec[5] if len(rec) > 5 else 4.0 * M * (N + K)
+    cnt = rec[6] if len(rec) > 6 else 1          # newer dumps: one record per (shape, bytes) class with the mean replay time
     key = (n.replace("cmgan_gemm_", "").replace("_f32", ""), M, N, K)
-    agg[key][0] += 1
-    agg[key][1] += us
-    agg[key][2] += nb
+    agg[key][0] += cnt
+    agg[key][1] += us * cnt
+    agg[key][2] += nb * cnt
 tot = sum(v[1] for v in agg.values())
 print(f"total GEMM time {tot / 1e3:.2f} ms over {len(d)} calls")
 for (n, M, N, K), (c, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
