@@ -343,9 +343,10 @@ def run_ours(args):
                            "algorithmic_gflop_per_step": f_rows / 1e9},
                 "wgrad": {"achieved": (b_wg / t_wg / 1e9) if t_wg > 0 else 0.0, "unit": "GB/s", "frac": (b_wg / t_wg / 1e9 / hbm_peak) if t_wg > 0 else 0.0,
                           "share_of_step": t_wg / step_s, "achieved_tflops": (f_wg / t_wg / 1e12) if t_wg > 0 else 0.0},
-                "traffic": 105.6e6,
-                "traffic_note": "dram read + write of one (129684 x 64) x (64 x 256) launch from ncu --set full (profiles/): 33.4 MB + 72.3 MB against "
-                                "166 MB algorithmic -- part of the output is still in the 126 MB L2 when the kernel ends"}
+                "traffic": 239.3e6,
+                "traffic_note": "dram read + write of the FFN-1 launch ((129684 x 64) x (64 x 256), Swish dual output; algorithmic 298.8 MB) from "
+                                "ncu --set full (profiles/ncu_r1_kernels.md): 33.4 MB + 205.9 MB -- part of the output is still in the 126 MB L2 "
+                                "when the kernel ends"}
 
     if rank == 0:
         out = {
