@@ -18,6 +18,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION prints a banner to stdout) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
