@@ -358,14 +358,17 @@ __global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_
         tc_fence_after();
         const int k = k0 + warp * 32 + lane;
         const bool bias_row = spare_row && k == g.Cin;
+        const bool bias_warp = spare_row && (g.Cin - k0) / 32 == warp;          // the warp whose lane 0 holds accumulator row k = Cin
+        // the bias row is staged in shared memory and added with full-line red.global: single-lane atomics from ~300 CTAs onto the
+        // same 8 cache lines serialise (~20 us); a warp-wide add of 32 consecutive floats is one L2 operation per line
+        float* bscr = reinterpret_cast<float*>(base_ptr + (sOnes - base));      // the ones block is dead once the accumulators are complete
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int n0 = 0; n0 < NB; n0 += 16) {
             float acc[16];
             tmem_ld16(trow + (uint32_t)n0, acc);
             if (bias_row) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
+                for (int j = 0; j < 16; ++j) bscr[n0 + j] = acc[j];
             }
             if (k < g.Cin) {
                 float* dst = g.C + (long)tap * g.sb_tap + (long)k * g.sb_k;
@@ -374,16 +377,21 @@ __global__ void __launch_bounds__(NT_TMA, 2) gemm_wgrad_tma_kernel(const __grid_
                     if (n0 + j < g.N) atomicAdd(dst + (long)(n0 + j) * g.sb_n, acc[j]);
             }
         }
+        if (bias_warp) {
+            __syncwarp();
+            for (int n = lane; n < g.N; n += 32) atomicAdd(g.dbias + n, bscr[n]);
+        }
         if (ones_mma && warp == 0) {
             for (int n0 = 0; n0 < NB; n0 += 16) {
                 float acc[16];
                 tmem_ld16(trow + (uint32_t)(NB + n0), acc);
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < g.N) atomicAdd(g.dbias + n0 + j, acc[j]);
+                    for (int j = 0; j < 16; ++j) bscr[n0 + j] = acc[j];
                 }
             }
+            __syncwarp();
+            for (int n = lane; n < g.N; n += 32) atomicAdd(g.dbias + n, bscr[n]);
         }
         tc_fence_before();
     }

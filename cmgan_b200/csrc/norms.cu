@@ -226,6 +226,55 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ x, long ldx, co
     }
 }
 
+// same, 128-bit loads: thread = (row-subgroup, 4 channels); C, ldx, ldd, tstride multiples of 4, 16-byte aligned pointers
+__global__ void norm_bwd_reduce4_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dact, long ldd,
+                                        long rows_per_group, int C, int chunk, int act, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, long tstride, const float* __restrict__ slope,
+                                        double* __restrict__ S, float* __restrict__ dslope) {
+    __shared__ float sm[256][12];
+    const int grp = blockIdx.y, cv = C / 4;
+    const long r_beg = (long)blockIdx.x * chunk;
+    const long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
+    const int c4 = threadIdx.x % cv, rg = threadIdx.x / cv, nrg = blockDim.x / cv;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, s3[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rg < nrg) {
+        const long t = (long)grp * tstride + c4 * 4;
+        const float4 sc4 = __ldg(reinterpret_cast<const float4*>(scale + t)), sh4 = __ldg(reinterpret_cast<const float4*>(shift + t));
+        const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + t)), rs4 = __ldg(reinterpret_cast<const float4*>(rstd + t));
+        float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (act) a4 = __ldg(reinterpret_cast<const float4*>(slope + c4 * 4));
+        const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w}, mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+        const float rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const long rb = (long)grp * rows_per_group;
+#pragma unroll 4
+        for (long r = r_beg + rg; r < r_end; r += nrg) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(x + (rb + r) * ldx) + c4);
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dact + (rb + r) * ldd) + c4);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float z = fmaf(v[j], sc[j], sh[j]);
+                float gq = d[j];
+                if (act && z < 0.f) { gq = d[j] * a[j]; s3[j] = fmaf(d[j], z, s3[j]); }
+                s1[j] += gq; s2[j] = fmaf(gq, (v[j] - mu[j]) * rs[j], s2[j]);
+            }
+        }
+    }
+    float* o = sm[threadIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[j] = s1[j]; o[4 + j] = s2[j]; o[8 + j] = s3[j]; }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x, cc = c >> 2, j = c & 3;
+        double a1 = 0, a2 = 0, a3 = 0;
+        for (int g = 0; g < nrg; ++g) { a1 += sm[g * cv + cc][j]; a2 += sm[g * cv + cc][4 + j]; a3 += sm[g * cv + cc][8 + j]; }
+        atomicAdd(S + ((long)grp * C + c) * 2, a1);
+        atomicAdd(S + ((long)grp * C + c) * 2 + 1, a2);
+        if (act && dslope) atomicAdd(dslope + c, (float)a3);
+    }
+}
+
 // backward pass 2.  dx = scale * (g - [train] (S1/n + xhat*S2/n));  also dgamma[c] += S2, dbeta[c] += S1 (first chunk of each group)
 // Block = one chunk of rows of one group; thread = (row-subgroup, channel): the per-(group, channel) constants are loaded once.
 __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dact, long ldd,
@@ -252,6 +301,51 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, con
         const float z = v * sc + sh;
         const float gq = (act && z < 0.f) ? d * a : d;
         dx[(rb + r) * lddx + c] = sc * (gq - m1 - (v - mu) * rs * m2);
+    }
+}
+
+// same, 128-bit accesses: thread = (row-subgroup, 4 channels)
+__global__ void norm_bwd_apply4_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dact, long ldd,
+                                       long rows_per_group, int C, int chunk, int act, int use_batch_stats,
+                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, long tstride,
+                                       const float* __restrict__ slope, const double* __restrict__ S,
+                                       float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int grp = blockIdx.y, cv = C / 4;
+    const long r_beg = (long)blockIdx.x * chunk;
+    const long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
+    const int c4 = threadIdx.x % cv, rg = threadIdx.x / cv, nrg = blockDim.x / cv;
+    if (rg >= nrg) return;
+    const long t = (long)grp * tstride + c4 * 4;
+    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(scale + t)), sh4 = __ldg(reinterpret_cast<const float4*>(shift + t));
+    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + t)), rs4 = __ldg(reinterpret_cast<const float4*>(rstd + t));
+    float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (act) a4 = __ldg(reinterpret_cast<const float4*>(slope + c4 * 4));
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w}, mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+    const float rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+    float m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 * 4 + j;
+        const double s1 = S[((long)grp * C + c) * 2], s2 = S[((long)grp * C + c) * 2 + 1];
+        if (blockIdx.x == 0 && rg == 0 && dgamma) { atomicAdd(dgamma + c, (float)s2); atomicAdd(dbeta + c, (float)s1); }
+        m1[j] = use_batch_stats ? (float)(s1 / (double)rows_per_group) : 0.f;
+        m2[j] = use_batch_stats ? (float)(s2 / (double)rows_per_group) : 0.f;
+    }
+    const long rb = (long)grp * rows_per_group;
+#pragma unroll 4
+    for (long r = r_beg + rg; r < r_end; r += nrg) {
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(x + (rb + r) * ldx) + c4);
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dact + (rb + r) * ldd) + c4);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float z = fmaf(v[j], sc[j], sh[j]);
+            const float gq = (act && z < 0.f) ? d[j] * a[j] : d[j];
+            o[j] = sc[j] * (gq - m1[j] - (v[j] - mu[j]) * rs[j] * m2[j]);
+        }
+        *reinterpret_cast<float4*>(dx + (rb + r) * lddx + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -406,6 +500,15 @@ CMGAN_API int cmgan_norm_bwd_reduce(const float* x, long long ldx, const float* 
     CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S, "cmgan_norm_bwd_reduce: null pointer");
     CMGAN_REQUIRE(C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_bwd_reduce: C=%d unsupported", C);
     if (G == 0 || rows_per_group == 0) return 0;
+    if (C % 4 == 0 && ldx % 4 == 0 && ldd % 4 == 0 && tstride % 4 == 0 &&
+        ((((uintptr_t)x) | ((uintptr_t)dact) | ((uintptr_t)scale) | ((uintptr_t)shift) | ((uintptr_t)mean) | ((uintptr_t)rstd) | ((uintptr_t)slope)) & 15) == 0) {
+        const int nrg4 = 256 / (C / 4);
+        const int chunk4 = nrg4 * 16;
+        dim3 grid4(cdiv(rows_per_group, chunk4), G);
+        norm_bwd_reduce4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, C, chunk4, act, scale, shift, mean, rstd,
+                                                                        tstride, slope, S, dslope);
+        return cmgan_check_launch("norm_bwd_reduce4_kernel");
+    }
     int nrg = 256 / C;
     int chunk = nrg * 64;
     dim3 grid(cdiv(rows_per_group, chunk), G);
@@ -421,6 +524,16 @@ CMGAN_API int cmgan_norm_bwd_apply(const float* x, long long ldx, const float* d
     CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S && dx, "cmgan_norm_bwd_apply: null pointer");
     CMGAN_REQUIRE(C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_bwd_apply: C=%d unsupported", C);
     if (G == 0 || rows_per_group == 0) return 0;
+    if (C % 4 == 0 && ldx % 4 == 0 && ldd % 4 == 0 && lddx % 4 == 0 && tstride % 4 == 0 &&
+        ((((uintptr_t)x) | ((uintptr_t)dact) | ((uintptr_t)dx) | ((uintptr_t)scale) | ((uintptr_t)shift) | ((uintptr_t)mean) | ((uintptr_t)rstd) |
+          ((uintptr_t)slope)) & 15) == 0) {
+        const int nrg4 = 256 / (C / 4);
+        const int chunk4 = nrg4 * 16;
+        dim3 grid4(cdiv(rows_per_group, chunk4), G);
+        norm_bwd_apply4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, C, chunk4, act, use_batch_stats, scale, shift,
+                                                                       mean, rstd, tstride, slope, S, dx, lddx, dgamma, dbeta);
+        return cmgan_check_launch("norm_bwd_apply4_kernel");
+    }
     const int nrg = 256 / C;
     const int chunk = nrg * 32;
     dim3 grid(cdiv(rows_per_group, chunk), G);
