@@ -111,6 +111,14 @@ class _Sink(dict):
 
 
 def disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
+    side, ops.WGRAD_STREAM = ops.WGRAD_STREAM, None      # the spectral-norm backward consumes each dW right away: keep these launches in order
+    try:
+        return _disc_bwd(S, dout, P, G, need_dx, need_dy)
+    finally:
+        ops.WGRAD_STREAM = side
+
+
+def _disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
     dev = dout.device
     if G is None:
         G = _Sink(P)

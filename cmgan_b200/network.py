@@ -57,9 +57,9 @@ def dense_block_bwd(cat, raws, tabs, dcat, P, G, p, B, T, Fw, sums: _Sums):
     """dcat slot 0 holds the gradient wrt act(out4); on return dcat slot 4 holds the gradient wrt the block input."""
     dev = cat.device
     M, rows = B * T * Fw, T * Fw
-    draw = _empty(M, C, dev=dev)
     for i in range(4, 0, -1):
         dil, c0, Cin, co = 2 ** (i - 1), (5 - i) * C, C * i, (4 - i) * C
+        draw = _empty(M, C, dev=dev)        # one per layer: the weight-gradient GEMM may still be reading it on the side stream
         _norm_bwd(raws[i - 1], C, (dcat, co), CAT, B, rows, C, 1, True, tabs[i - 1], 0, P[f"{p}.prelu{i}.weight"], draw, C,
                   G[f"{p}.norm{i}.weight"], G[f"{p}.norm{i}.bias"], G[f"{p}.prelu{i}.weight"], sums)
         taps = _dense_taps(dil)
@@ -207,3 +207,4 @@ def tscnet_bwd(S: dict, dfr, dfi, P, G: Dict[str, torch.Tensor]):
     _norm_bwd(S["raw0"], C, (dcatE, 4 * C), CAT, B, T * F, C, 1, True, S["tab0"], 0, P[pe + ".conv_1.2.weight"], draw1, C,
               G[pe + ".conv_1.1.weight"], G[pe + ".conv_1.1.bias"], G[pe + ".conv_1.2.weight"], sums)
     call("cmgan_head_conv_wgrad", x, xs[0], xs[1], xs[2], xs[3], B, T, F, draw1, C, G[pe + ".conv_1.0.weight"], G[pe + ".conv_1.0.bias"])
+    ops.join_wgrad()        # weight-gradient GEMMs launched on the side stream (ops.WGRAD_STREAM) are complete from here on

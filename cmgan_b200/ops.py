@@ -18,6 +18,8 @@ _KERNELS = {"cmgan_attention_bwd": 3, "cmgan_attention_bwd_tf32": 2}
 LAUNCHES = 0
 PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" else 0   # default for every dense contraction
 SEED_DEV = None  # optional uint64 device counter added to every dropout seed (set by the trainer for CUDA-graph replay)
+WGRAD_STREAM = None   # optional side stream: weight-gradient GEMMs run there, concurrently with the data-gradient chain (join_wgrad)
+_WGRAD_KEEP = []      # operands of in-flight side-stream launches (kept allocated until the join)
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
 PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
@@ -47,6 +49,13 @@ def call(name: str, *args) -> None:
     conv = [ptr(a) if (a is None or isinstance(a, (torch.Tensor, tuple))) else a for a in args]
     lib().call(name, *conv, stream())
     LAUNCHES += _KERNELS.get(name, 1)
+
+
+def join_wgrad() -> None:
+    """the current stream waits for every weight-gradient launch issued on the side stream (end of a backward pass)"""
+    if WGRAD_STREAM is not None:
+        torch.cuda.current_stream().wait_stream(WGRAD_STREAM)
+    _WGRAD_KEEP.clear()
 
 
 def set_precision(mode: str) -> None:
@@ -112,7 +121,16 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
         a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
     global LAUNCHES
     name = "cmgan_gemm_wgrad_f32" if wgrad else "cmgan_gemm_rows_f32"
-    lib().call(name, ctypes.byref(a), stream())
+    if wgrad and WGRAD_STREAM is not None and PROBE is None:
+        # parameter gradients feed nothing until the optimiser: launch on the side stream behind an event on the current one
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        WGRAD_STREAM.wait_event(ev)
+        lib().call(name, ctypes.byref(a), WGRAD_STREAM.cuda_stream)
+        _WGRAD_KEEP.append((A, D, C, dbias, p0, p1, p2))
+    else:
+        lib().call(name, ctypes.byref(a), stream())
     if PROBE is not None:       # bench.py: record every GEMM launch of one instrumented step so that it can be replayed back to back
         # algorithmic bytes of the launch: A read once (not once per tap), C written, every auxiliary operand of the epilogue read once
         # (residual / saved activation / accumulated C), the second output of the dual epilogue, the weights; wgrad: A and D read once

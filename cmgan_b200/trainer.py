@@ -10,6 +10,8 @@ PESQ itself is host code of the reference (discriminator.py:9-26) and stays outs
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -51,6 +53,8 @@ class _Adam:
 class FusedTrainer:
     def __init__(self, model: TSCNet, disc: Optional[Discriminator] = None, lr: float = 5e-4, weights=(0.1, 0.9, 0.2, 0.05), seed: int = 0):
         self.model, self.disc, self.w = model, disc, weights
+        if ops.WGRAD_STREAM is None and os.environ.get("CMGAN_WGRAD_STREAM", "1") != "0":
+            ops.WGRAD_STREAM = torch.cuda.Stream()        # weight-gradient GEMMs overlap the data-gradient chain (also inside the CUDA graph)
         self.pg = _flatten_params(model)
         self.gg = model.enable_flat_grads()
         self.opt_g = _Adam(self.pg, self.gg, lr)                      # train.py:63
