@@ -173,6 +173,33 @@ def test_layernorm_fwd_bwd():
     _chk(db, b.grad, 1e-5, "ln_bwd dbeta")
 
 
+def test_layernorm_bwd_dropout_scaled_copy():
+    """cmgan_ln_bwd_drop: dx as cmgan_ln_bwd, plus dz = alpha * mask * dx with the mask of the GEMM epilogue that applied the dropout
+    (cmgan_dropout_mask of the same seed over the (M, 64) element index)"""
+    from cmgan_b200.ops import drop_params
+    M, seed, p, alpha = 389, 1234567, 0.3, 0.5
+    xd, dy, r1 = _rand(M, 64, seed=50).to(DEV), _rand(M, 64, seed=51).to(DEV), _rand(M, 64, seed=52).to(DEV)
+    g = (_rand(64, seed=53) + 1.2).to(DEV)
+    st = torch.empty(M, 2, device=DEV)
+    call("cmgan_ln_stats", xd, 64, M, st)
+    dx0, dx1, dz = (torch.full((M, 64), float("nan"), device=DEV) for _ in range(3))
+    dg0, db0, dg1, db1 = (torch.zeros(64, device=DEV) for _ in range(4))
+    call("cmgan_ln_bwd", dy, 64, xd, 64, st, g, M, r1, 64, None, 0, dx0, 64, dg0, db0)
+    thr, inv = drop_params(p)
+    call("cmgan_ln_bwd_drop", dy, 64, xd, 64, st, g, M, r1, 64, None, 0, dx1, 64, dg1, db1, dz, 64, alpha, seed, thr, inv, None)
+    mask = torch.empty(M * 64, device=DEV)
+    call("cmgan_dropout_mask", mask, M * 64, seed, thr)          # 0 / 1 keep decisions
+    torch.cuda.synchronize()
+    assert torch.equal(dx0, dx1)
+    _chk(dg1, dg0, 1e-5, "ln_bwd_drop dgamma")      # block-level atomics: same sums, any order
+    _chk(db1, db0, 1e-5, "ln_bwd_drop dbeta")
+    kept = (mask > 0).float().mean().item()
+    assert abs(kept - (1 - p)) < 0.02
+    _chk(dz, (alpha * inv * mask.view(M, 64) * dx1).double(), 1e-6, "ln_bwd_drop dz")
+    call("cmgan_ln_bwd_drop", dy, 64, xd, 64, st, g, M, r1, 64, None, 0, dx1, 64, dg1, db1, dz, 64, alpha, seed, 0, 1.0, None)
+    _chk(dz, (alpha * dx1).double(), 1e-6, "ln_bwd_drop dz (no dropout)")
+
+
 @pytest.mark.parametrize("Cn,G,rows,act", [(64, 2, 777, 1), (1, 3, 500, 1), (128, 1, 900, 0), (16, 2, 300, 1)])
 def test_group_norm_fwd_bwd(Cn, G, rows, act):
     x = (_rand(G * rows, Cn, seed=40) * 2.0 + 0.7).double().requires_grad_(True)
