@@ -18,8 +18,16 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION prints a banner to stdout) goes to stderr
+# stdout carries exactly one JSON line.  Libraries print there too (NCCL's version banner), so file descriptor 1 is pointed at
+# stderr for the whole run and the JSON line is written to the saved original descriptor by emit().
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_STDOUT_FD, (json.dumps(obj) + "\n").encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -162,7 +170,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = 1.0 / dt
     sample = "1 utterance (B=1 x 2 s) per step of the B=4 workload, oracle CPU port of the reference forward+backward, fp32, torch CPU threads = cores"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.batch), "reference_sample": sample},
@@ -372,7 +380,7 @@ def run_ours(args):
             dt = time_cpu_baseline(1, 0)
             out["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "1 step of B=1 x 2 s (same loss) through the oracle CPU port of the reference, fp32, all host threads"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
