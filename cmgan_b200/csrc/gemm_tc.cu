@@ -1,20 +1,25 @@
 // tf32 tensor-core implementation of the row-parallel GEMM contract (gemm_args.h) for sm_100a.
-// Persistent, warp-specialised: one CTA per SM loops over 128-row output tiles; the accumulator lives in TMEM and is
-// double-buffered so that the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// Persistent, warp-specialised: each CTA loops over 128-row output tiles; the accumulator lives in TMEM and is double-buffered so
+// that the epilogue of tile i overlaps the loads and MMAs of tile i+1.  Two shapes: 2 CTAs/SM x 10 warps (4 epilogue warps) for
+// narrow N, 1 CTA/SM x 14 warps (8 epilogue warps) otherwise.
 //
-//   warps 0-3  A producers.
-//              * no prologue (convolutions / projections over materialised activations, data gradients): cp.async (LDGSTS, 16 B,
-//                zero-fill for padding rows) straight into the canonical K-major SWIZZLE_128B layout, pipelined two chunks deep;
-//                a chunk is published with cp.async.wait_group -> fence.proxy.async -> mbarrier.arrive.
-//              * with prologue (BatchNorm+Swish / Swish+dropout / dropout / LayerNorm): LDG.128 -> registers -> transform ->
-//                round to tf32 -> st.shared -> fence.proxy.async -> mbarrier.arrive.
+//   warps 0-3  A producers, three modes:
+//              * TMA (cfg.tma = 1): dense row-major A, one thread issues cp.async.bulk.tensor.2d boxes of 128 rows x 32 floats that
+//                land directly in the K-major SWIZZLE_128B layout; rows past M are zero-filled by the unit.
+//              * TMA patches (cfg.tma = 2, template PATCH): same-size convolutions; a tile is a 16 x 8 (h x w) patch of one image and
+//                a chunk is one (tap, 32 channels) box of a 4-D (C, W, H, B) tensor map with the tap's (dy, dx) added to the
+//                coordinates -- padding is the unit's out-of-bounds zero fill.
+//                With TMA every stage of the ring is in flight; LDGSTS producers saturate near 16 GB/s per SM.
+//              * cp.async (LDGSTS 16 B, zero fill) for strided / transposed convolutions, and LDG -> registers -> transform ->
+//                st.shared for operands with a prologue (BatchNorm+Swish / Swish+dropout / dropout / LayerNorm / InstanceNorm+PReLU).
 //   warp 4     TMEM allocation (2 x N columns); one lane issues tcgen05.mma (kind::tf32, M = 128, N = 16..256, K = 8) and
 //              tcgen05.commit (A-stage release, accumulator ready).
-//   warp 5     weight tiles by cp.async.bulk (TMA bulk copy, UBLKCP) of pre-tiled, pre-swizzled (N x 128 B) blocks: all K chunks
-//              once per CTA when the whole weight fits in shared memory ("resident", every conformer GEMM), else per K chunk
-//              through the same stage ring as A ("streamed", the dilated dense convolutions).
-//   warps 6-9  epilogue: tcgen05.ld 32x32b -> per-warp shared-memory staging -> coalesced float4 rows: bias, dropout, residual,
-//              activation gradients, Swish dual output -> global; then release the accumulator buffer.
+//   warp 5     weight tiles by cp.async.bulk (UBLKCP) of pre-tiled, pre-swizzled (N x 128 B) blocks: all K chunks once per CTA when
+//              the whole weight fits in shared memory ("resident", every conformer GEMM), else per K chunk through the stage ring
+//              ("streamed", the dilated dense convolutions).
+//   warps 6+   epilogue (compile-time kind): two tcgen05.ld 32x32b.x16 in flight -> per-warp shared-memory staging -> coalesced
+//              float4 rows: bias, dropout, residual, activation gradients, Swish dual output -> global; auxiliary operands are
+//              prefetched one to two 8-row batches ahead; then the accumulator buffer is released.
 //
 // The weight operand is re-tiled once per call by pack_b_kernel into the scratch the caller passes (any source layout:
 // Linear (N,K), Conv2d (N,C,kh,kw), and the transposed forms used for data gradients).
