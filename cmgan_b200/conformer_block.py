@@ -27,6 +27,11 @@ def _empty(*shape, dev, dtype=torch.float32):
     return torch.empty(*shape, dtype=dtype, device=dev)
 
 
+def _adjacent(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """b starts exactly where the contiguous tensor a ends (consecutive segments of a flat parameter / gradient buffer)"""
+    return a.is_contiguous() and b.is_contiguous() and b.data_ptr() == a.data_ptr() + a.numel() * a.element_size()
+
+
 class _Tabs:
     """scale/shift/mean/rstd per (group, channel) and PReLU slope per channel of a normalisation site"""
 
@@ -116,8 +121,12 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
     # ---- attention (ref: conformer.py:90-133)
     xn2, st2 = layer_norm(x1, f"{p}.attn.norm.weight", f"{p}.attn.norm.bias")
     qkv = _empty(M, 3 * C, dev=dev)
-    gemm(A=xn2, lda=C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, C=qkv, ldc=3 * C, M=M, N=C, Cin=C)
-    gemm(A=xn2, lda=C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, C=(qkv, C), ldc=3 * C, M=M, N=2 * C, Cin=C)
+    Wq, Wkv = P[f"{p}.attn.fn.to_q.weight"], P[f"{p}.attn.fn.to_kv.weight"]
+    if _adjacent(Wq, Wkv):      # flat parameter buffer: [Wq; Wkv] is one (192, 64) matrix -> one projection instead of two
+        gemm(A=xn2, lda=C, W=Wq, sb_k=1, sb_n=C, C=qkv, ldc=3 * C, M=M, N=3 * C, Cin=C)
+    else:
+        gemm(A=xn2, lda=C, W=Wq, sb_k=1, sb_n=C, C=qkv, ldc=3 * C, M=M, N=C, Cin=C)
+        gemm(A=xn2, lda=C, W=Wkv, sb_k=1, sb_n=C, C=(qkv, C), ldc=3 * C, M=M, N=2 * C, Cin=C)
     ctx = _empty(M, C, dev=dev)
     lse = _empty(M, 4, dev=dev)
     call("cmgan_attention_fwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_fwd", qkv, P[f"{p}.attn.fn.rel_pos_emb.weight"], B, T, F2, axis,
@@ -222,11 +231,16 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     call("cmgan_attention_bwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_bwd", S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv,
          G[f"{p}.attn.fn.rel_pos_emb.weight"])
     dln2 = _empty(M, C, dev=dev)
-    gemm(A=dqkv, lda=3 * C, W=P[f"{p}.attn.fn.to_q.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=C)
-    gemm(A=(dqkv, C), lda=3 * C, W=P[f"{p}.attn.fn.to_kv.weight"], sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=2 * C, epi=EPI_ACC, alpha=1.0)
-    gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=dqkv, ldd=3 * C, N=C, W=None, C=G[f"{p}.attn.fn.to_q.weight"], sb_k=1, sb_n=C, ldc=0, M=M)
-    gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=(dqkv, C), ldd=3 * C, N=2 * C, W=None, C=G[f"{p}.attn.fn.to_kv.weight"], sb_k=1, sb_n=C, ldc=0,
-         M=M)
+    Wq, Wkv = P[f"{p}.attn.fn.to_q.weight"], P[f"{p}.attn.fn.to_kv.weight"]
+    Gq, Gkv = G[f"{p}.attn.fn.to_q.weight"], G[f"{p}.attn.fn.to_kv.weight"]
+    if _adjacent(Wq, Wkv) and _adjacent(Gq, Gkv):      # merged (192, 64) projection (see conformer_fwd)
+        gemm(A=dqkv, lda=3 * C, W=Wq, sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=3 * C)
+        gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=dqkv, ldd=3 * C, N=3 * C, W=None, C=Gq, sb_k=1, sb_n=C, ldc=0, M=M)
+    else:
+        gemm(A=dqkv, lda=3 * C, W=Wq, sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=C)
+        gemm(A=(dqkv, C), lda=3 * C, W=Wkv, sb_k=C, sb_n=1, C=dln2, ldc=C, M=M, N=C, Cin=2 * C, epi=EPI_ACC, alpha=1.0)
+        gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=dqkv, ldd=3 * C, N=C, W=None, C=Gq, sb_k=1, sb_n=C, ldc=0, M=M)
+        gemm(wgrad=True, A=S["xn2"], lda=C, Cin=C, D=(dqkv, C), ldd=3 * C, N=2 * C, W=None, C=Gkv, sb_k=1, sb_n=C, ldc=0, M=M)
     dx1, dz1 = ln_bwd(dln2, S["x1"], S["st2"], f"{p}.attn.norm", dx2, None, zalpha=0.5, zseed=sd[1], zp=dp)
     # ---- first feed-forward; the outer residual adds dy
     return ff_bwd(dx1, dz1, S["x"], S["f1"], "ff1", sd[0], res2=dy)[0]

@@ -171,7 +171,10 @@ def test_flat_grad_mode_matches(g_weights, golden):
         fr, fi = m(x)
         (fr.square().mean() + fi.abs().mean()).backward()
         grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
+    gmax = max(v.abs().max().item() for v in grads[0].values())
     for k in grads[0]:
         ref = grads[0][k]
         err = (grads[1][k] - ref).abs().max().item()
-        assert err <= 1e-4 * max(ref.abs().max().item(), 1e-3), f"{k}: {err}"      # atomics reorder sums: not bit-exact
+        # atomics reorder sums: not bit-exact.  Biases in front of an InstanceNorm have a mathematically zero gradient (pure rounding
+        # noise ~1e-7), hence the floor relative to the largest gradient of the network.
+        assert err <= 1e-4 * max(ref.abs().max().item(), 1e-3, 1e-4 * gmax), f"{k}: {err}"
