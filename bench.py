@@ -180,8 +180,8 @@ def run_reference(args):
 
 
 def workload_name(B):
-    return (f"generator fwd+bwd (train mode: dropout + BatchNorm batch stats), stft->compress->TSCNet->uncompress->istft->loss, "
-            f"batch {B} x 2 s @16 kHz per GPU, fp32 storage")
+    return (f"generator training step fwd+bwd+AdamW (train mode: dropout + BatchNorm batch stats), "
+            f"stft->compress->TSCNet->uncompress->istft->loss->backward->update, batch {B} x 2 s @16 kHz per GPU, fp32 storage")
 
 
 # ------------------------------------------------------------------------------------------------ our arm (GPU)
@@ -212,8 +212,8 @@ def run_ours(args):
     clean, noisy = synth_batch(B, 1000 + rank, device=dev)
     hclean, hnoisy = synth_batch(B, 1000 + rank, pin=True)
 
-    def step(c, n):          # eager: every kernel launched from Python
-        return trainer.generator_step(c, n, update=False)
+    def step(c, n):          # eager: every kernel launched from Python (gradient all-reduce when N > 1, AdamW update)
+        return trainer.generator_step(c, n, update=True)
 
     def barrier():
         if world > 1:
@@ -245,13 +245,16 @@ def run_ours(args):
     eager_host_ms = host_ms[0]
     # ---- the whole step as one CUDA graph (the gradient all-reduce stays an eager NCCL call when N > 1)
     l0 = ops.LAUNCHES
-    trainer.capture_generator_step(clean, noisy, update=False, allreduce=False)
-    launches_per_step = (ops.LAUNCHES - l0) // 3           # 2 warm-up passes + 1 capture pass
+    # N = 1: forward, losses, backward and the AdamW update are all inside the graph.  N > 1: the graph ends with the backward pass,
+    # then the NCCL all-reduce of the flat gradient buffer and the (single-kernel) AdamW update are issued eagerly.
+    trainer.capture_generator_step(clean, noisy, update=(world == 1), allreduce=False)
+    launches_per_step = (ops.LAUNCHES - l0) // 3 + (1 if world > 1 else 0)      # 2 warm-up passes + 1 capture pass
 
     def gstep(c, n):
         loss = trainer.replay_generator_step(c, n)
         if world > 1:
             parallel.allreduce_mean_(flat)
+            trainer.opt_g.step()
         return loss
 
     for _ in range(3):
@@ -260,6 +263,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms = timed(lambda: gstep(clean, noisy), args.steps)
+    loss_after = float(gstep(clean, noisy).item())
+    assert loss_after == loss_after and abs(loss_after) < 1e30, f"training step diverged: loss {loss_after}"
     launches = launches_per_step * args.steps
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
@@ -365,7 +370,9 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(B), "global_batch": B * world, "clip_samples": CLIP, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
-                       "weights": "torch.manual_seed(0) default init", "launch": "one CUDA graph per step (cmgan_b200.trainer.FusedTrainer)"},
+                       "weights": "torch.manual_seed(0) default init, updated by AdamW every step (lr 5e-4)", "loss_after": loss_after,
+                       "launch": "one CUDA graph per step (cmgan_b200.trainer.FusedTrainer): forward, losses, backward, AdamW"
+                                 + (" -- all-reduce + AdamW eager after the graph" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * CLIP * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "eager": {"value": world * B * args.steps / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager / args.steps,
