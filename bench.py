@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the CMGAN hot path on B200 (contract in the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload train_gd|gen_only]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json metric: utterances/sec, 2 s @ 16 kHz, generator forward+backward): per rank, one step =
-RMS normalise -> STFT -> power compression -> TSCNet forward (train mode: dropout, BatchNorm batch statistics) ->
-un-compression -> iSTFT -> generator loss (RI + magnitude + time terms) -> backward through all of it into the flat
-gradient buffer (+ one NCCL all-reduce of that buffer when N > 1), on a batch of B = 4 synthetic 2 s clips (train.py's
-default batch size and configs[1]'s batch).  Prints ONE JSON line on rank 0.
+Workload (BASELINE.json configs[2], metric: utterances/sec, 2 s @ 16 kHz): per rank, one step = the reference's whole
+``train_step`` (train.py:176-205) on a batch of B = 16 synthetic 2 s clips:
+  generator: RMS normalise -> STFT -> power compression -> TSCNet forward (train mode: dropout, BatchNorm batch statistics) ->
+  un-compression -> iSTFT -> loss (RI + magnitude + time + metric-GAN term through the discriminator) -> backward through all of it ->
+  (one NCCL all-reduce of the flat gradient buffer when N > 1) -> AdamW;
+  discriminator: D(clean, est) and D(clean, clean) forward (train mode: spectral-norm power iterations, dropout), loss against a
+  fixed synthetic PESQ target (the ``pesq`` package is host code and absent), backward, (all-reduce), AdamW.
+All of it is one CUDA graph per step.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -29,6 +32,7 @@ os.dup2(2, 1)
 def emit(obj) -> None:
     os.write(_STDOUT_FD, (json.dumps(obj) + "\n").encode())
 
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -38,6 +42,8 @@ UNIT = "utt/s"
 CLIP = 32000
 FWD_GFLOP_PER_UTT = 145.96            # mm + bmm + conv, 2*MAC, 2 s clip
 STEP_GFLOP_PER_UTT = 3 * FWD_GFLOP_PER_UTT
+TSCB_FWD_GFLOP_PER_UTT = 4 * 19.58    # four two-stage conformer blocks
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def _peaks():
@@ -106,27 +112,102 @@ def synth_batch(B, seed, device=None, pin=False):
     return clean, noisy
 
 
-# ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_step(sd, clean, noisy):
-    """the oracle's (= the reference algorithm's) generator forward+backward on CPU, same loss as the GPU arm"""
-    import torch
-    import torch.nn.functional as F
-    from oracle import cmgan_oracle as O
-    for v in sd.values():
-        if v.is_floating_point() and v.grad is not None:
-            v.grad = None
-    go = O.forward_generator_step(clean, noisy, sd, training=True)    # BatchNorm batch statistics as in train mode
-    loss = 0.1 * (F.mse_loss(go["est_real"], go["clean_real"]) + F.mse_loss(go["est_imag"], go["clean_imag"])) \
-        + 0.9 * F.mse_loss(go["est_mag"], go["clean_mag"]) + 0.2 * torch.mean(torch.abs(go["est_audio"] - clean))
-    loss.backward()
-    return loss.item()
+def workload_name(B, kind):
+    if kind == "gen_only":
+        return (f"generator training step fwd+bwd+AdamW (train mode: dropout + BatchNorm batch stats), "
+                f"stft->compress->TSCNet->uncompress->istft->loss->backward->update, batch {B} x 2 s @16 kHz per GPU, fp32 storage")
+    return (f"configs[2]: train.py train_step = generator fwd+bwd+AdamW (train mode, loss incl. the metric-GAN term through D) + discriminator step "
+            f"(2 more D forwards, 2 D backwards, AdamW; fixed synthetic PESQ target 0.5), batch {B} x 2 s @16 kHz per GPU, "
+            f"tf32 tensor-core operands / fp32 storage + accumulation")
 
 
-def cpu_weights():
-    import torch
-    from oracle import cmgan_oracle as O
-    w = O.load_weights_npz(os.path.join(ROOT, "tests", "golden", "weights_g.npz"))
-    return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in w.items()}
+# ------------------------------------------------------------------------------------------------ reference arms
+class RefModules:
+    """The reference's own generator / discriminator (unmodified files staged under baseline/_ref by tools/stage_reference.py) driven
+    by the train.py:72-151 glue restated with the torch >= 2 complex STFT API; when the staged files are
+    absent, the oracle port (oracle/cmgan_oracle.py) stands in.  Used by ``--impl reference`` (CPU) and ``gpu_eager_reference``."""
+
+    def __init__(self, device, with_disc=True):
+        import torch
+        from oracle import cmgan_oracle as O
+        self.torch, self.O, self.dev = torch, O, device
+        w = O.load_weights_npz(os.path.join(ROOT, "tests", "golden", "weights_g.npz"))
+        self.kind = "port"
+        self.model = self.disc = None
+        if os.path.isdir(os.path.join(REF_DIR, "models")):
+            try:
+                import types
+                if "pesq" not in sys.modules:           # discriminator.py imports pesq at module level; the bench never calls it
+                    stub = types.ModuleType("pesq")
+                    stub.pesq = lambda *a, **k: 0.0
+                    sys.modules["pesq"] = stub
+                sys.path.insert(0, REF_DIR)
+                from models.generator import TSCNet
+                import utils as ref_utils
+                self.ref_utils = ref_utils
+                self.model = TSCNet(num_channel=64, num_features=201)
+                self.model.load_state_dict(w, strict=True)
+                self.model = self.model.to(device).train()
+                if with_disc:
+                    from models.discriminator import Discriminator
+                    torch.manual_seed(7)
+                    self.disc = Discriminator(ndf=16).to(device).train()
+                self.kind = "reference"
+            except Exception as e:       # noqa: BLE001 -- report and fall back to the port
+                print(f"[bench] staged reference modules unusable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+                self.model = self.disc = None
+                self.kind = "port"
+        if self.model is None:
+            self.sd = {k: (v.clone().to(device).requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.to(device)) for k, v in w.items()}
+            self.params = [v for v in self.sd.values() if v.is_floating_point() and v.requires_grad]
+        else:
+            self.params = list(self.model.parameters())
+
+    def _stft(self, x):
+        t = self.torch
+        return t.view_as_real(t.stft(x, 400, 100, window=t.hamming_window(400, device=x.device), onesided=True, return_complex=True))
+
+    def _istft(self, spec):
+        t = self.torch
+        return t.istft(t.view_as_complex(spec.contiguous()), 400, 100, window=t.hamming_window(400, device=spec.device), onesided=True)
+
+    def gen_fwd(self, clean, noisy):
+        t, F = self.torch, self.torch.nn.functional
+        if self.model is None:
+            go = self.O.forward_generator_step(clean, noisy, self.sd, training=True)
+        else:
+            c = t.sqrt(noisy.size(-1) / t.sum(noisy ** 2.0, dim=-1))
+            n2, c2 = (noisy.t() * c).t(), (clean.t() * c).t()
+            nspec = self.ref_utils.power_compress(self._stft(n2)).permute(0, 1, 3, 2)
+            cspec = self.ref_utils.power_compress(self._stft(c2))
+            er, ei = self.model(nspec)
+            er, ei = er.permute(0, 1, 3, 2), ei.permute(0, 1, 3, 2)
+            go = dict(est_real=er, est_imag=ei, est_mag=t.sqrt(er ** 2 + ei ** 2), clean_real=cspec[:, 0:1], clean_imag=cspec[:, 1:2],
+                      clean_mag=t.sqrt(cspec[:, 0:1] ** 2 + cspec[:, 1:2] ** 2),
+                      est_audio=self._istft(self.ref_utils.power_uncompress(er, ei).squeeze(1)))
+        loss = 0.1 * (F.mse_loss(go["est_real"], go["clean_real"]) + F.mse_loss(go["est_imag"], go["clean_imag"])) \
+            + 0.9 * F.mse_loss(go["est_mag"], go["clean_mag"]) + 0.2 * t.mean(t.abs(go["est_audio"] - clean))
+        return go, loss
+
+    def step(self, clean, noisy, with_disc):
+        """generator forward + backward (+ the GAN term and the discriminator's loss/backward when the reference D is available)"""
+        t, F = self.torch, self.torch.nn.functional
+        for p in self.params:
+            p.grad = None
+        go, loss = self.gen_fwd(clean, noisy)
+        B = clean.shape[0]
+        if with_disc and self.disc is not None:
+            fake = self.disc(go["clean_mag"], go["est_mag"])
+            loss = loss + 0.05 * F.mse_loss(fake.flatten(), t.ones(B, device=clean.device))
+        loss.backward()
+        if with_disc and self.disc is not None:
+            for p in self.disc.parameters():
+                p.grad = None
+            d_enh = self.disc(go["clean_mag"], go["est_mag"].detach())
+            d_max = self.disc(go["clean_mag"], go["clean_mag"])
+            dl = F.mse_loss(d_max.flatten(), t.ones(B, device=clean.device)) + F.mse_loss(d_enh.flatten(), t.full((B,), 0.5, device=clean.device))
+            dl.backward()
+        return loss
 
 
 def host_threads():
@@ -139,49 +220,37 @@ def host_threads():
     return max(1, min(n, 32))
 
 
-def time_cpu_baseline(n_steps=1, warm=0):
+def time_cpu(n_steps, warm, with_disc=True):
     import torch
     torch.set_num_threads(host_threads())
-    sd = cpu_weights()
+    ref = RefModules(torch.device("cpu"), with_disc)
     clean, noisy = synth_batch(1, 123)
     for _ in range(warm):
-        cpu_reference_step(sd, clean, noisy)
+        ref.step(clean, noisy, with_disc)
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        cpu_reference_step(sd, clean, noisy)
-    dt = (time.perf_counter() - t0) / n_steps
-    return dt
+        ref.step(clean, noisy, with_disc)
+    return (time.perf_counter() - t0) / n_steps, ref.kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     cores = host_threads()
-    torch.set_num_threads(cores)
-    sd = cpu_weights()
-    clean, noisy = synth_batch(1, 123)
-    for _ in range(args.warmup):
-        cpu_reference_step(sd, clean, noisy)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(sd, clean, noisy)
-    dt = (time.perf_counter() - t0) / args.steps
+    with_disc = args.workload == "train_gd"
+    dt, kind = time_cpu(args.steps, args.warmup, with_disc)
     v = 1.0 / dt
-    sample = "1 utterance (B=1 x 2 s) per step of the B=4 workload, oracle CPU port of the reference forward+backward, fp32, torch CPU threads = cores"
+    sample = ("1 utterance (B=1 x 2 s) per step of the workload: " + ("the reference's own TSCNet / Discriminator modules (baseline/_ref)" if kind == "reference"
+              else "oracle CPU port of the reference") + ", generator forward+backward" + (" + discriminator step" if with_disc and kind == "reference" else "")
+              + ", fp32, torch CPU threads = cores")
     emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch), "reference_sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.batch, args.workload), "reference_sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
-
-
-def workload_name(B):
-    return (f"generator training step fwd+bwd+AdamW (train mode: dropout + BatchNorm batch stats), "
-            f"stft->compress->TSCNet->uncompress->istft->loss->backward->update, batch {B} x 2 s @16 kHz per GPU, fp32 storage")
 
 
 # ------------------------------------------------------------------------------------------------ our arm (GPU)
@@ -192,7 +261,7 @@ def run_ours(args):
     from cmgan_b200 import ops as _ops
     _ops.set_precision(args.precision)
     from cmgan_b200 import ops, training
-    from cmgan_b200.ops import call
+    from cmgan_b200.trainer import FusedTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,17 +272,19 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     B = args.batch
+    gd = args.workload == "train_gd"
     torch.manual_seed(0)
     model = cmgan_b200.TSCNet(64, 201).to(dev).train()
-    from cmgan_b200.trainer import FusedTrainer
-    from cmgan_b200 import parallel
-    trainer = FusedTrainer(model, None)          # flat parameter/gradient buffers; rank-0 parameters win (train.py:68)
-    flat = trainer.gg
+    disc = cmgan_b200.Discriminator(16).to(dev).train() if gd else None
+    trainer = FusedTrainer(model, disc)          # flat parameter/gradient buffers; rank-0 parameters win (train.py:68)
     clean, noisy = synth_batch(B, 1000 + rank, device=dev)
     hclean, hnoisy = synth_batch(B, 1000 + rank, pin=True)
+    pesq_t = torch.full((B,), 0.5, device=dev)
+    hpesq = torch.full((B,), 0.5).pin_memory()
 
-    def step(c, n):          # eager: every kernel launched from Python (gradient all-reduce when N > 1, AdamW update)
-        return trainer.generator_step(c, n, update=True)
+    def eager_step(c, n):          # every kernel launched from Python (gradient all-reduce when N > 1, AdamW updates)
+        lg = trainer.generator_step(c, n)
+        return (lg, trainer.discriminator_step(pesq_t)) if gd else (lg, None)
 
     def barrier():
         if world > 1:
@@ -239,81 +310,187 @@ def run_ours(args):
             ms = t.item()
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step(clean, noisy)
-    ms_eager = timed(lambda: step(clean, noisy), args.steps)
+    for _ in range(2):
+        eager_step(clean, noisy)
+    K_eager = min(args.steps, 3)
+    ms_eager = timed(lambda: eager_step(clean, noisy), K_eager) / K_eager
     eager_host_ms = host_ms[0]
-    # ---- the whole step as one CUDA graph (the gradient all-reduce stays an eager NCCL call when N > 1)
+
+    # ---- the whole step as one CUDA graph.  N > 1: the NCCL all-reduces (generator: two segments, the first overlapped with the encoder's
+    # backward; discriminator: one) and both AdamW updates are captured too; CMGAN_GRAPH_NCCL=0 keeps them eager after a backward-only graph.
+    graph_nccl = world == 1 or os.environ.get("CMGAN_GRAPH_NCCL", "1") != "0"
     l0 = ops.LAUNCHES
-    # N = 1: forward, losses, backward and the AdamW update are all inside the graph.  N > 1: the graph ends with the backward pass,
-    # then the NCCL all-reduce of the flat gradient buffer and the (single-kernel) AdamW update are issued eagerly.
-    trainer.capture_generator_step(clean, noisy, update=(world == 1), allreduce=False)
-    launches_per_step = (ops.LAUNCHES - l0) // 3 + (1 if world > 1 else 0)      # 2 warm-up passes + 1 capture pass
+    if gd:
+        if graph_nccl:
+            trainer.capture_train_step(clean, noisy)
+        else:
+            raise SystemExit("the G+D workload needs the collectives inside the graph (CMGAN_GRAPH_NCCL=1)")
+    else:
+        trainer.capture_generator_step(clean, noisy, update=graph_nccl, allreduce=graph_nccl)
+    launches_per_step = trainer.graph_launches
 
-    def gstep(c, n):
+    def gstep(c, n, p=None):
+        if gd:
+            return trainer.replay_train_step(c, n, p)
         loss = trainer.replay_generator_step(c, n)
-        if world > 1:
-            parallel.allreduce_mean_(flat)
+        if not graph_nccl:
+            from cmgan_b200 import parallel
+            parallel.allreduce_mean_(trainer.gg)
             trainer.opt_g.step()
-        return loss
+            if trainer.pack is not None:
+                trainer.pack.refresh()
+        return loss, None
 
-    for _ in range(3):
-        gstep(clean, noisy)
+    for _ in range(max(args.warmup, 3)):
+        gstep(clean, noisy, pesq_t)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(lambda: gstep(clean, noisy), args.steps)
-    loss_after = float(gstep(clean, noisy).item())
+    ms = timed(lambda: gstep(clean, noisy, pesq_t), args.steps)
+    losses = gstep(clean, noisy, pesq_t)
+    loss_after = float(losses[0].item())
+    dloss_after = float(losses[1].item()) if gd else None
     assert loss_after == loss_after and abs(loss_after) < 1e30, f"training step diverged: loss {loss_after}"
     launches = launches_per_step * args.steps
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- end to end: pinned host buffers in, loss scalar out, every step
-    host_loss = torch.empty(1).pin_memory()
+    # ---- end to end: pinned host buffers in (waveforms + PESQ targets), loss scalars out, every step
+    host_loss = torch.empty(2).pin_memory()
 
     def e2e_step():
-        loss = gstep(hclean, hnoisy)                     # H2D copies of the pinned batch into the graph's input buffers
-        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller reads the loss every step (train.py:205)
+        lg, ld = gstep(hclean, hnoisy, hpesq)             # H2D copies of the pinned batch into the graph's input buffers
+        host_loss[0:1].copy_(lg.detach().reshape(1), non_blocking=True)
+        if ld is not None:
+            host_loss[1:2].copy_(ld.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the losses every step (train.py:205)
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = 2 * B * CLIP * 4 + (B * 4 if gd else 0)
+    d2h = 8 if gd else 4
 
-    # ---- forward only (configs[1]: eval forward, batch 4), also as a CUDA graph
-    model.eval()
-    with torch.no_grad():
-        def fwd_only():
-            go = training.forward_generator_step(model, clean, noisy)
-            return go["est_audio"]
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": workload_name(B, args.workload), "global_batch": B * world, "clip_samples": CLIP, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
+                       "weights": "torch.manual_seed(0) default init, updated by AdamW every step (lr 5e-4 / 1e-3)", "loss_after": loss_after,
+                       "disc_loss_after": dloss_after,
+                       "launch": "one CUDA graph per step (cmgan_b200.trainer.FusedTrainer): forward, losses, backward, "
+                                 + ("NCCL gradient all-reduces, " if world > 1 and graph_nccl else "") + "AdamW"
+                                 + ("" if graph_nccl else " -- all-reduce + AdamW eager after the graph")},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "eager": {"value": world * B / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager,
+                      "host_enqueue_ms_per_step": eager_host_ms, "note": "same step launched kernel by kernel from Python (no CUDA graph)"},
+            "clocks": clocks,
+            "model_tflops": value * STEP_GFLOP_PER_UTT / 1e3,
+        }
+    if world == 1 and not args.no_extras:
+        extras(args, out, trainer, model, dev, ms / args.steps)
+    if rank == 0:
+        emit(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(args, out, trainer, model, dev, step_ms):
+    """single-GPU explanatory numbers: forward-only (configs[1]), the TSCB stack's roofline, the GEMM family's roofline, the same-box
+    GPU-eager reference, the CPU baseline"""
+    import torch
+    from cmgan_b200 import conformer_block as G, ops, training
+    peaks, psrc = _peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6500.0)
+    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0      # dense tf32 = half the bf16 rate on the same tensor pipe
+
+    def time_graph(fn, reps):
+        """capture ``fn`` (after two warm-up passes) and time ``reps`` replays with CUDA events"""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                fwd_only()
+                fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        fgraph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(fgraph):
-            fwd_out = fwd_only()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
         for _ in range(2):
-            fgraph.replay()
-        ms_f = timed(fgraph.replay, args.steps)
-    fwd_value = world * B * args.steps / (ms_f * 1e-3)
-    model.train()
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
 
-    # ---- dominant kernel family: every GEMM launch of one step is recorded (arguments + operands kept alive) and the whole list is
+    # ---- forward only (configs[1]: eval forward, batch 4)
+    Bf = 4
+    clean4, noisy4 = synth_batch(Bf, 77, device=dev)
+    model.eval()
+    with torch.no_grad():
+        ms_f = time_graph(lambda: training.forward_generator_step(model, clean4, noisy4)["est_audio"], args.steps)
+    model.train()
+    out["forward_only"] = {"value": Bf / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f, "workload": f"configs[1]: eval forward, batch {Bf} x 2 s"}
+
+    # ---- the TSCB stack alone (the kernel group the north-star puts a number on): 8 conformer blocks forward + backward, train mode,
+    # on the bench batch's (B, 321, 101, 64) activation, as one graph; algorithmic flops = SURVEY 8(d) 4 x 19.58 GFLOP forward per utterance, x3
+    B = args.batch
+    T, F2 = CLIP // 100 + 1, 101
+    M = B * T * F2
+    P = model._tensor_dict()
+    h0 = torch.randn(M, 64, device=dev)
+    dy0 = torch.randn(M, 64, device=dev)
+    grads = trainer.model._flat_views
+    cache = trainer.pack
+
+    def tscb_stack():
+        ops.PACK_CACHE = cache
+        try:
+            sums = G._Sums(8 * 2 * 128 * 2 * 2 + 64, dev)
+            saves, h = [], h0
+            for i in range(1, 5):
+                for axis, name in ((0, "time_conformer"), (1, "freq_conformer")):
+                    sv = {}
+                    h = G.conformer_fwd(h, P, f"TSCB_{i}.{name}", B, T, F2, axis, True, 1, (i - 1) * 2 + axis, sums, sv)
+                    saves.append(sv)
+            d = dy0
+            sums2 = G._Sums(8 * 2 * 128 * 2 * 2 + 64, dev)
+            for sv in reversed(saves):
+                d = G.conformer_bwd(d, sv, P, grads, B, T, F2, sums2)
+            ops.join_wgrad()
+            return d
+        finally:
+            ops.PACK_CACHE = None
+    bufs = [b.clone() for b in model.buffers()]
+    ms_tscb = time_graph(tscb_stack, max(3, args.steps // 2))
+    for b, v in zip(model.buffers(), bufs):
+        b.copy_(v)
+    tscb_flop = 3 * TSCB_FWD_GFLOP_PER_UTT * B * 1e9
+    out["tscb"] = {"what": "4 x TSCB (8 conformer blocks) forward + backward, train mode, one CUDA graph, CUDA events", "batch": B, "ms": ms_tscb,
+                   "share_of_step": ms_tscb / step_ms, "algorithmic_gflop": tscb_flop / 1e9, "achieved_tflops": tscb_flop / (ms_tscb * 1e-3) / 1e12,
+                   "peak_tflops": tf32_peak, "frac_of_tensor_roofline": tscb_flop / (ms_tscb * 1e-3) / 1e12 / tf32_peak,
+                   "peak_source": f"{psrc}: bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)", "target": 0.70}
+
+    # ---- dominant kernel family: every GEMM launch of one generator step is recorded (arguments + operands kept alive) and the whole list is
     # replayed back to back between two CUDA events, so the durations carry no host gaps (an eager step is host-bound)
-    ops.PROBE = []
-    step(clean, noisy)
-    torch.cuda.synchronize()
-    probe, ops.PROBE = ops.PROBE, None
     import ctypes as _ct
     from cmgan_b200._lib import lib as _lib
+    clean, noisy = synth_batch(B, 1000, device=dev)
+    ops.PROBE = []
+    trainer.generator_step(clean, noisy, update=False)
+    torch.cuda.synchronize()
+    probe, ops.PROBE = ops.PROBE, None
 
     def replay(entries, reps=3):
         L, st = _lib(), ops.stream()
+
         def once():
             for p in entries:
                 L.call(p[0], _ct.byref(p[5]), st)
@@ -330,7 +507,7 @@ def run_ours(args):
     rows = [p for p in probe if p[0] == "cmgan_gemm_rows_f32"]
     wgs = [p for p in probe if p[0] == "cmgan_gemm_wgrad_f32"]
     t_rows, t_wg = replay(rows), replay(wgs)
-    if os.environ.get("CMGAN_PROBE_DUMP") and rank == 0:      # per-shape replay timings for analysis (not part of the JSON line)
+    if os.environ.get("CMGAN_PROBE_DUMP"):      # per-shape replay timings for analysis (not part of the JSON line)
         shapes = {}
         for p in probe:
             shapes.setdefault((p[0], p[1], p[2], p[3], p[4]), []).append(p)
@@ -342,54 +519,62 @@ def run_ours(args):
     b_rows = float(sum(p[4] for p in rows))
     b_wg = float(sum(p[4] for p in wgs))
     del probe
-    peaks, psrc = _peaks()
-    hbm_peak = peaks.get("hbm_gbs", 6500.0)
-    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0      # dense tf32 = half the bf16 rate on the same tensor pipe
-    step_s = ms / args.steps * 1e-3
+    step_s = step_ms * 1e-3
     achieved = b_rows / t_rows / 1e9 if t_rows > 0 else 0.0
+    traffic, traffic_note = None, "no ncu capture committed for this round yet"
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tp):           # dram read + write per launch of the dominant kernel, parsed from a committed ncu --set full report
+        tj = json.load(open(tp))
+        traffic, traffic_note = tj.get("traffic_bytes_per_launch"), tj.get("note", "")
     # The dominant kernel family is the row-parallel GEMM (tcgen05 tf32): K = 64 .. 256 against N = 64 .. 256 is 13 - 64 flop/byte,
     # far below the ~110 flop/byte balance point of tf32 tensor cores vs HBM, so the family is HBM-bound and is reported as such.
-    roofline = {"bound": "hbm", "kernel": "gemm_rows_tc_kernel (every dense contraction of the step: linear, pointwise, dilated/strided conv)",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": f"{psrc}: hbm_gbs (copy bandwidth, read + write)",
-                "how": "sum of algorithmic bytes (A once, C, epilogue operands, weights) over every launch of one step / CUDA-event time of those "
-                       "launches replayed back to back (each includes its ~3 us weight re-tiling kernel)",
-                "launches_per_step": len(rows), "share_of_step": t_rows / step_s, "algorithmic_gb_per_step": b_rows / 1e9,
-                "tensor": {"achieved_tflops": f_rows / t_rows / 1e12 if t_rows > 0 else 0.0, "peak_tflops": tf32_peak,
-                           "algorithmic_gflop_per_step": f_rows / 1e9},
-                "wgrad": {"achieved": (b_wg / t_wg / 1e9) if t_wg > 0 else 0.0, "unit": "GB/s", "frac": (b_wg / t_wg / 1e9 / hbm_peak) if t_wg > 0 else 0.0,
-                          "share_of_step": t_wg / step_s, "achieved_tflops": (f_wg / t_wg / 1e12) if t_wg > 0 else 0.0},
-                "traffic": 239.3e6,
-                "traffic_note": "dram read + write of the FFN-1 launch ((129684 x 64) x (64 x 256), Swish dual output; algorithmic 298.8 MB) from "
-                                "ncu --set full (profiles/ncu_r1_kernels.md): 33.4 MB + 205.9 MB -- part of the output is still in the 126 MB L2 "
-                                "when the kernel ends"}
+    out["roofline"] = {"bound": "hbm", "kernel": "gemm_rows_tc_kernel (every dense contraction of the generator step: linear, pointwise, dilated/strided conv)",
+                       "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                       "peak_source": f"{psrc}: hbm_gbs (copy bandwidth, read + write)",
+                       "how": "sum of algorithmic bytes (A once, C, epilogue operands, weights) over every launch of one generator step / CUDA-event time of "
+                              "those launches replayed back to back",
+                       "launches_per_step": len(rows), "share_of_step": t_rows / step_s, "algorithmic_gb_per_step": b_rows / 1e9,
+                       "tensor": {"achieved_tflops": f_rows / t_rows / 1e12 if t_rows > 0 else 0.0, "peak_tflops": tf32_peak,
+                                  "algorithmic_gflop_per_step": f_rows / 1e9},
+                       "wgrad": {"achieved": (b_wg / t_wg / 1e9) if t_wg > 0 else 0.0, "unit": "GB/s", "frac": (b_wg / t_wg / 1e9 / hbm_peak) if t_wg > 0 else 0.0,
+                                 "share_of_step": t_wg / step_s, "achieved_tflops": (f_wg / t_wg / 1e12) if t_wg > 0 else 0.0},
+                       "traffic": traffic, "traffic_note": traffic_note}
 
-    if rank == 0:
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": workload_name(B), "global_batch": B * world, "clip_samples": CLIP, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
-                       "weights": "torch.manual_seed(0) default init, updated by AdamW every step (lr 5e-4)", "loss_after": loss_after,
-                       "launch": "one CUDA graph per step (cmgan_b200.trainer.FusedTrainer): forward, losses, backward, AdamW"
-                                 + (" -- all-reduce + AdamW eager after the graph" if world > 1 else "")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * CLIP * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
-            "eager": {"value": world * B * args.steps / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager / args.steps,
-                      "host_enqueue_ms_per_step": eager_host_ms, "note": "same step launched kernel by kernel from Python (no CUDA graph)"},
-            "clocks": clocks,
-            "roofline": roofline,
-            "forward_only": {"value": fwd_value, "unit": UNIT, "ms_per_step": ms_f / args.steps, "workload": f"configs[1]: eval forward, batch {B} x 2 s"},
-            "model_tflops": value * STEP_GFLOP_PER_UTT / 1e3,
-        }
-        if world == 1 and not args.no_cpu:
-            cores = host_threads()
-            dt = time_cpu_baseline(1, 0)
-            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": "1 step of B=1 x 2 s (same loss) through the oracle CPU port of the reference, fp32, all host threads"}
-        emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    # ---- the same-box competitor (SURVEY 8d / BASELINE.md 4.5): the reference's modules in PyTorch eager on this B200, generator forward +
+    # backward, B = 4, fp32 and with TF32 allowed
+    if not args.no_gpu_eager:
+        try:
+            ref = RefModules(dev, with_disc=False)
+            cl, nz = synth_batch(4, 55, device=dev)
+            res = {}
+            for name, flag in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = flag
+                torch.backends.cudnn.allow_tf32 = flag
+                for _ in range(2):
+                    ref.step(cl, nz, False)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    ref.step(cl, nz, False)
+                e1.record()
+                torch.cuda.synchronize()
+                res[name] = {"value": 4 * 3 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / 3}
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = True
+            out["gpu_eager_reference"] = {"kind": ref.kind, "workload": "generator forward + backward (train mode), batch 4 x 2 s, PyTorch eager on this GPU",
+                                          **res}
+            del ref
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            out["gpu_eager_reference"] = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    if not args.no_cpu:
+        cores = host_threads()
+        dt, kind = time_cpu(2, 1, with_disc=args.workload == "train_gd")
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": "2 timed steps (after 1 warm-up) of B=1 x 2 s of the same workload through "
+                                         + ("the reference's own modules (baseline/_ref)" if kind == "reference" else "the oracle CPU port") + ", fp32, all host threads"}
 
 
 def main():
@@ -398,8 +583,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU (configs[2]: 16; configs[3] = 8 per GPU on 8 GPUs)")
+    ap.add_argument("--workload", default="train_gd", choices=["train_gd", "gen_only"],
+                    help="train_gd: generator + discriminator train step (configs[2], default); gen_only: generator step without the GAN term")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the GPU-eager reference leg")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (no forward-only / roofline / baseline legs)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="dense contractions: tcgen05 tf32 (default) or exact fp32 FFMA")
     args = ap.parse_args()
     if args.impl == "reference":

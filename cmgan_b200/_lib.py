@@ -40,6 +40,7 @@ class GemmArgs(ctypes.Structure):
         ("ws", ctypes.c_void_p), ("ws_floats", ctypes.c_longlong),
         ("C2", ctypes.c_void_p), ("ldc2", ctypes.c_longlong),
         ("seed_dev", ctypes.c_void_p),
+        ("b_packed", ctypes.c_int),
     ]
 
 

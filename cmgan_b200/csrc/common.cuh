@@ -49,6 +49,16 @@ __host__ __device__ __forceinline__ uint32_t cmgan_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
+// effective seed of a dropout site at graph replay `counter`: a 64-bit mix (splitmix64 finaliser) of the site seed and the device step counter,
+// so that neighbouring sites / consecutive steps never share a mask function (seed + counter would alias site i at step n+1 with site i+1 at step n)
+__host__ __device__ __forceinline__ uint64_t cmgan_mix_seed(uint64_t seed, uint64_t counter) {
+    uint64_t z = seed ^ (counter * 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return z;
+}
+__device__ __forceinline__ uint64_t cmgan_eff_seed(uint64_t seed, const unsigned long long* __restrict__ seed_dev) {
+    return seed_dev ? cmgan_mix_seed(seed, __ldg(seed_dev)) : seed;
+}
 __host__ __device__ __forceinline__ uint32_t cmgan_seed32(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u); }
 __host__ __device__ __forceinline__ uint32_t cmgan_pair_hash(uint32_t seed32, uint64_t pair) { return cmgan_mix32(((uint32_t)pair * 0x9E3779B1u) ^ seed32); }
 // returns 0 (dropped) or 1/(1-p) (kept); thr = p * 2^32 (0 => dropout disabled => 1); the decision uses the top 16 bits of thr

@@ -56,4 +56,10 @@ typedef struct CmganGemmArgs {
     float* ws; long long ws_floats;   // tf32 path: scratch for the re-tiled weight operand, >= N_pad * Cin * ntaps floats (caller-owned)
     float* C2; long long ldc2;        // second output of CMGAN_EPI_SWISH_DUAL
     const unsigned long long* seed_dev;   // optional device counter added to both dropout seeds (CUDA-graph replays draw fresh masks)
+    int b_packed;              // tf32 path: 1 = ws already holds the re-tiled weight (cmgan_pack_weights after the optimiser step), skip the re-tiling
 } CmganGemmArgs;
+
+// one weight to re-tile for the tensor-core path (cmgan_pack_weights): same meaning as the B / sb_* / Cin / ntaps / N fields above
+typedef struct CmganPackDesc {
+    const float* src; float* dst; long long sb_tap, sb_k, sb_n; long long Cin, ntaps, N;
+} CmganPackDesc;

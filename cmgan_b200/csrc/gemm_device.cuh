@@ -7,8 +7,8 @@
 namespace cmgan_gemm {
 
 // dropout seeds: the per-site constant plus an optional device-resident step counter
-__device__ __forceinline__ unsigned long long eff_seed(const CmganGemmArgs& g) { return g.seed + (g.seed_dev ? __ldg(g.seed_dev) : 0ull); }
-__device__ __forceinline__ unsigned long long eff_pro_seed(const CmganGemmArgs& g) { return g.pro_seed + (g.seed_dev ? __ldg(g.seed_dev) : 0ull); }
+__device__ __forceinline__ unsigned long long eff_seed(const CmganGemmArgs& g) { return cmgan_eff_seed(g.seed, g.seed_dev); }
+__device__ __forceinline__ unsigned long long eff_pro_seed(const CmganGemmArgs& g) { return cmgan_eff_seed(g.pro_seed, g.seed_dev); }
 
 struct RowInfo { int b, y, x; bool ok; };
 

@@ -63,6 +63,21 @@ __global__ void pack_b_kernel(const float* __restrict__ B, long sb_tap, long sb_
     out[(chunk * BN + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
 }
 
+// every weight of a network in one launch (after the optimiser step): blockIdx.y = descriptor
+__global__ void pack_all_kernel(const CmganPackDesc* __restrict__ descs) {
+    const CmganPackDesc d = descs[blockIdx.y];
+    const int Cin = (int)d.Cin, N = (int)d.N;
+    const long total = d.ntaps * (Cin / KC) * (long)N * KC;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int kk = (int)(i % KC); long t = i / KC; int n = (int)(t % N); long chunk = t / N;
+        int cpt = Cin / KC;
+        int tap = (int)(chunk / cpt), kc = (int)(chunk % cpt);
+        float v = to_tf32(__ldg(d.src + (long)tap * d.sb_tap + (long)(kc * KC + kk) * d.sb_k + (long)n * d.sb_n));
+        int c = kk >> 2, j = kk & 3;
+        d.dst[(chunk * N + n) * KC + ((c ^ (n & 7)) << 2) + j] = v;
+    }
+}
+
 // tma: 0 = cp.async / register producers, 1 = dense 2-D tensor map, 2 = same-size convolution: tiles are 16 x 8 (h x w) patches of one image
 // (pw = 8 positions along w, ph = 16 lines), fetched through a 4-D tensor map with the tap offset added to the coordinates
 struct TcCfg { int BN, stages, tmem_cols, resident, ntiles, tma, nfx, nty, W, H; };
@@ -551,9 +566,11 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
             }
         }
     }
-    long total = (long)nchunks * cfg.BN * KC;
-    pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
-    if (cmgan_check_launch("pack_b_kernel")) return -1;
+    if (!a->b_packed) {
+        long total = (long)nchunks * cfg.BN * KC;
+        pack_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(a->B, a->sb_tap, a->sb_k, a->sb_n, a->Cin, a->ntaps, a->N, cfg.BN, a->ws);
+        if (cmgan_check_launch("pack_b_kernel")) return -1;
+    }
     const int grid = cfg.ntiles < ctas * g_num_sms ? cfg.ntiles : ctas * g_num_sms;
     const int variant = a->pro != CMGAN_PRO_NONE ? 0 : (epi8 ? 1 : 2);
     int rc = -2;
@@ -584,4 +601,13 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
     if (rc == -2) { cmgan_set_error("gemm_rows_tc: unknown epilogue %d", a->epi); return -1; }
     if (rc) return -1;
     return cmgan_check_launch("gemm_rows_tc_kernel");
+}
+
+// Re-tile n weights (device table of CmganPackDesc) for the tensor-core path in one launch: called once after the optimiser step, so that the
+// GEMM launches of the next step find their B operand ready (CmganGemmArgs.b_packed = 1).
+CMGAN_API int cmgan_pack_weights(const CmganPackDesc* descs, int n, void* stream) {
+    CMGAN_REQUIRE(descs || n == 0, "cmgan_pack_weights: null table");
+    if (n == 0) return 0;
+    pack_all_kernel<<<dim3(48, n), 256, 0, (cudaStream_t)stream>>>(descs);
+    return cmgan_check_launch("pack_all_kernel");
 }

@@ -432,7 +432,7 @@ bool make_map32(CUtensorMap* tm, int rank, const float* ptr, long long cols, lon
 // dbias[n] += sum_m prod(D[m, n])
 __global__ void colsum_kernel(const float* __restrict__ D, long ldd, long M, int N, int prod, float alpha, unsigned long long seed, unsigned thr,
                               float inv_keep, int rows_per_block, float* __restrict__ out, const unsigned long long* __restrict__ seed_dev) {
-    if (seed_dev) seed += __ldg(seed_dev);
+    seed = cmgan_eff_seed(seed, seed_dev);
     __shared__ float sm[256];
     const int c = threadIdx.x % N, rg = threadIdx.x / N, nrg = blockDim.x / N;
     const long r_beg = (long)blockIdx.x * rows_per_block;

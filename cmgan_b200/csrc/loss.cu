@@ -100,9 +100,11 @@ __global__ void mag_bwd_add_kernel(const float* __restrict__ er, const float* __
 
 // AdamW over flat buffers (torch.optim.AdamW defaults: decoupled weight decay, bias correction)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float lr,
-                             float b1, float b2, float eps, float wd, float bc1, float bc2, const unsigned long long* __restrict__ step_dev) {
+                             float b1, float b2, float eps, float wd, float bc1, float bc2, const unsigned long long* __restrict__ step_dev,
+                             const float* __restrict__ lr_dev) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (lr_dev) lr = __ldg(lr_dev);        // learning rate as a device scalar: a schedule (StepLR, train.py:248-253) works under CUDA-graph replay
     if (step_dev) { float t = (float)__ldg(step_dev); bc1 = 1.f - powf(b1, t); bc2 = 1.f - powf(b2, t); }
     float gi = g[i], mi = m[i], vi = v[i], pi = p[i];
     pi *= 1.f - lr * wd;
@@ -156,10 +158,10 @@ CMGAN_API int cmgan_mag_bwd_add(const float* er, const float* ei, const float* d
 }
 
 CMGAN_API int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
-                          int step, const unsigned long long* step_dev, void* stream) {
+                          int step, const unsigned long long* step_dev, const float* lr_dev, void* stream) {
     CMGAN_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "cmgan_adamw: bad arguments");
     if (n == 0) return 0;
     float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-    adamw_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, step_dev);
+    adamw_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, step_dev, lr_dev);
     return cmgan_check_launch("adamw_kernel");
 }

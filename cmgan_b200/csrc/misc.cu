@@ -65,7 +65,7 @@ __device__ float block_sum(float v, float* sm) {
 }
 
 __global__ void spectral_norm_kernel(const float* __restrict__ W, int R, int Cc, float* __restrict__ u, float* __restrict__ v, int training,
-                                     float* __restrict__ w_sn, float* __restrict__ sigma_out) {
+                                     float* __restrict__ w_sn, float* __restrict__ sigma_out, float* __restrict__ uv_out) {
     __shared__ float sm[32];
     extern __shared__ float dyn[];      // su[R], sv[Cc], swv[R]
     float* su = dyn; float* sv = dyn + R; float* swv = sv + Cc;
@@ -110,6 +110,10 @@ __global__ void spectral_norm_kernel(const float* __restrict__ W, int R, int Cc,
     if (training) {
         for (int i = threadIdx.x; i < R; i += blockDim.x) u[i] = su[i];
         for (int j = threadIdx.x; j < Cc; j += blockDim.x) v[j] = sv[j];
+    }
+    if (uv_out) {       // the (u, v) this forward's sigma / W_sn were formed with: the backward of THIS forward must use them, not the live buffers
+        for (int i = threadIdx.x; i < R; i += blockDim.x) uv_out[i] = su[i];
+        for (int j = threadIdx.x; j < Cc; j += blockDim.x) uv_out[R + j] = sv[j];
     }
     if (threadIdx.x == 0) sigma_out[0] = sigma;
 }
@@ -157,7 +161,7 @@ __global__ void drop_prelu_kernel(const float* __restrict__ x, long n, int C, co
                                   unsigned thr, float inv_keep, float* __restrict__ y, const unsigned long long* __restrict__ seed_dev) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (seed_dev) seed += __ldg(seed_dev);
+    seed = cmgan_eff_seed(seed, seed_dev);
     float z = x[i] * cmgan_drop_scale(seed, (uint64_t)i, thr, inv_keep);
     y[i] = z >= 0.f ? z : z * slope[i % C];
 }
@@ -166,7 +170,7 @@ __global__ void drop_prelu_bwd_kernel(const float* __restrict__ x, const float* 
                                       const unsigned long long* __restrict__ seed_dev) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (seed_dev) seed += __ldg(seed_dev);
+    seed = cmgan_eff_seed(seed, seed_dev);
     float ds = cmgan_drop_scale(seed, (uint64_t)i, thr, inv_keep);
     float z = x[i] * ds;
     float g = dy[i];
@@ -225,11 +229,12 @@ CMGAN_API int cmgan_unstack2(const float* dxy, long long n, float* dx, float* dy
     return cmgan_check_launch("unstack2_kernel");
 }
 
-CMGAN_API int cmgan_spectral_norm(const float* W, int R, int Cc, float* u, float* v, int training, float* w_sn, float* sigma, void* stream) {
+CMGAN_API int cmgan_spectral_norm(const float* W, int R, int Cc, float* u, float* v, int training, float* w_sn, float* sigma, float* uv_out,
+                                  void* stream) {
     CMGAN_REQUIRE(W && u && v && w_sn && sigma && R > 0 && Cc > 0, "cmgan_spectral_norm: bad arguments");
     size_t smem = (size_t)(2 * R + Cc) * sizeof(float);
     CMGAN_REQUIRE(smem <= 40000, "cmgan_spectral_norm: matrix too large (%d x %d)", R, Cc);
-    spectral_norm_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(W, R, Cc, u, v, training, w_sn, sigma);
+    spectral_norm_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(W, R, Cc, u, v, training, w_sn, sigma, uv_out);
     return cmgan_check_launch("spectral_norm_kernel");
 }
 

@@ -64,7 +64,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const flo
     float2 ag = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
     // optional second output dz = zalpha * dropmask(zseed) * dx: the gradient entering the next residual branch, whose forward output
     // went through dropout (mask regenerated from the element index row * 64 + channel, as in the GEMM epilogue that applied it)
-    const uint32_t zs32 = dz ? cmgan_seed32(zseed + (seed_dev ? __ldg(seed_dev) : 0ull)) : 0u;
+    const uint32_t zs32 = dz ? cmgan_seed32(cmgan_eff_seed(zseed, seed_dev)) : 0u;
     const uint32_t zt16 = zthr >> 16;
     for (int i = 0; i < rows_per_warp; ++i) {
         long row = r0 + i;

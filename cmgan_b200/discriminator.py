@@ -29,17 +29,28 @@ DROP_P = 0.3
 
 
 def _spectral(P, key, training, dev):
-    """-> (w_sn, sigma): W / sigma with one power iteration in training (u, v updated in place)"""
+    """-> (w_sn, (sigma, uv)): W / sigma with one power iteration in training (the u / v buffers are updated in place, as by the
+    reference's hook); ``uv`` = [u | v] as used by THIS forward (torch's spectral_norm clones them per training forward, so the
+    backward of a forward is consistent with its own sigma even when a later forward has iterated the buffers again)"""
     w = P[key + ".weight_orig"]
     R = w.shape[0]
     Cc = w.numel() // R
     w_sn = _empty(*w.shape, dev=dev)
     sigma = _empty(1, dev=dev)
-    call("cmgan_spectral_norm", w, R, Cc, P[key + ".weight_u"], P[key + ".weight_v"], 1 if training else 0, w_sn, sigma)
-    return w_sn, sigma
+    uv = _empty(R + Cc, dev=dev)
+    call("cmgan_spectral_norm", w, R, Cc, P[key + ".weight_u"], P[key + ".weight_v"], 1 if training else 0, w_sn, sigma, uv)
+    return w_sn, (sigma, uv)
 
 
 def disc_fwd(x, y, P, training: bool, seed: int, save):
+    cache, ops.PACK_CACHE = ops.PACK_CACHE, None      # W / sigma is a fresh tensor every forward: nothing to cache
+    try:
+        return _disc_fwd(x, y, P, training, seed, save)
+    finally:
+        ops.PACK_CACHE = cache
+
+
+def _disc_fwd(x, y, P, training: bool, seed: int, save):
     dev = x.device
     B, one, H, W = x.shape
     assert one == 1 and y.shape == x.shape
@@ -90,10 +101,11 @@ def disc_fwd(x, y, P, training: bool, seed: int, save):
     return out
 
 
-def _sn_bwd(P, G, key, w_sn, dw_sn, sigma):
+def _sn_bwd(P, G, key, w_sn, dw_sn, sig_uv):
     w = P[key + ".weight_orig"]
     R = w.shape[0]
-    call("cmgan_spectral_norm_bwd", w_sn, dw_sn, R, w.numel() // R, P[key + ".weight_u"], P[key + ".weight_v"], sigma, G[key + ".weight_orig"])
+    sigma, uv = sig_uv
+    call("cmgan_spectral_norm_bwd", w_sn, dw_sn, R, w.numel() // R, uv, (uv, R), sigma, G[key + ".weight_orig"])
 
 
 class _Sink(dict):
@@ -112,10 +124,12 @@ class _Sink(dict):
 
 def disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
     side, ops.WGRAD_STREAM = ops.WGRAD_STREAM, None      # the spectral-norm backward consumes each dW right away: keep these launches in order
+    cache, ops.PACK_CACHE = ops.PACK_CACHE, None
     try:
         return _disc_bwd(S, dout, P, G, need_dx, need_dy)
     finally:
         ops.WGRAD_STREAM = side
+        ops.PACK_CACHE = cache
 
 
 def _disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
@@ -264,6 +278,14 @@ class Discriminator(nn.Module):
 
     def _grad_targets(self):
         if self._flat_views is not None:
+            # ``optimizer.zero_grad()`` (set_to_none=True by default) detaches p.grad from the flat buffer: re-attach the views and give
+            # the call its meaning (gradients start from zero) instead of silently accumulating into a buffer the optimiser no longer sees
+            named = dict(self.named_parameters())
+            if any(named[k].grad is None for k in self._param_keys):
+                from .ops import call
+                call("cmgan_fill", self.flat_grad, self.flat_grad.numel(), 0.0)
+                for k in self._param_keys:
+                    named[k].grad = self._flat_views[k]
             return self._flat_views, tuple(None for _ in self._param_keys)
         named = dict(self.named_parameters())
         G = {k: torch.zeros_like(named[k]) for k in self._param_keys}

@@ -16,6 +16,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from . import ops
 from .conformer_block import C
 from .network import tscnet_bwd, tscnet_fwd
 
@@ -176,6 +177,8 @@ class TSCNet(nn.Module):
         self._step = 0
         self.flat_grad: Optional[torch.Tensor] = None    # set by enable_flat_grads()
         self._flat_views: Optional[Dict[str, torch.Tensor]] = None
+        self._pack, self._pack_sig = ops.PackCache(), None
+        self._weights_epoch = 0          # bumped by FusedTrainer whenever its kernels update the parameters behind PyTorch's back
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _tensor_dict(self) -> Dict[str, torch.Tensor]:
@@ -201,6 +204,14 @@ class TSCNet(nn.Module):
     def _grad_targets(self):
         """(name -> tensor the kernels accumulate into, tuple returned to autograd for *params)"""
         if self._flat_views is not None:
+            # ``optimizer.zero_grad()`` (set_to_none=True by default) detaches p.grad from the flat buffer: re-attach the views and give
+            # the call its meaning (gradients start from zero) instead of silently accumulating into a buffer the optimiser no longer sees
+            named = dict(self.named_parameters())
+            if any(named[k].grad is None for k in self._param_keys):
+                from .ops import call
+                call("cmgan_fill", self.flat_grad, self.flat_grad.numel(), 0.0)
+                for k in self._param_keys:
+                    named[k].grad = self._flat_views[k]
             return self._flat_views, tuple(None for _ in self._param_keys)
         named = dict(self.named_parameters())
         G = {k: torch.zeros_like(named[k]) for k in self._param_keys}
@@ -215,4 +226,16 @@ class TSCNet(nn.Module):
             self._step += 1
             torch._foreach_add_([b for k, b in self.named_buffers() if k.endswith("num_batches_tracked")], 1)   # bookkeeping only
         params = [p for _, p in self.named_parameters()]
+        if not self.training and not torch.is_grad_enabled() and ops.PACK_CACHE is None:
+            # inference with frozen weights: keep the re-tiled tensor-core copies of the weights between calls; any in-place change of a
+            # parameter through PyTorch (load_state_dict, an optimiser) bumps its version counter and drops the cache
+            sig = (params[0].data_ptr(), sum(p._version for p in params), self._weights_epoch)
+            if sig != self._pack_sig:
+                self._pack.clear()
+                self._pack_sig = sig
+            ops.PACK_CACHE = self._pack
+            try:
+                return _TSCNetFn.apply(x, self, self.training, self.seed * 7919 + self._step, *params)
+            finally:
+                ops.PACK_CACHE = None
         return _TSCNetFn.apply(x, self, self.training, self.seed * 7919 + self._step, *params)

@@ -134,9 +134,10 @@ def tscnet_fwd(x, P, training: bool, seed: int, save: Optional[dict]):
     return fr, fi
 
 
-def tscnet_bwd(S: dict, dfr, dfi, P, G: Dict[str, torch.Tensor]):
+def tscnet_bwd(S: dict, dfr, dfi, P, G: Dict[str, torch.Tensor], after_tscb=None):
     """Backward of tscnet_fwd.  dfr / dfi: gradients wrt final_real / final_imag ((B,1,T,F), any strides, or None).
-    Parameter gradients are accumulated (+=) into the tensors of G."""
+    Parameter gradients are accumulated (+=) into the tensors of G.  ``after_tscb`` (optional callable) runs once the decoders'
+    and the TSCB stack's gradients are complete (the trainer starts their all-reduce there, under the encoder's backward)."""
     x = S["x"]
     dev = x.device
     B, T, F, F2 = S["B"], S["T"], S["F"], S["F2"]
@@ -191,6 +192,8 @@ def tscnet_bwd(S: dict, dfr, dfi, P, G: Dict[str, torch.Tensor]):
         for axis in (1, 0):
             dh = conformer_bwd(dh, S["conf"][k], P, G, B, T, F2, sums)
             k -= 1
+    if after_tscb is not None:
+        after_tscb()
     # ---- encoder
     pe = "dense_encoder"
     catE, tab2 = S["catE"], S["tab2"]

@@ -20,12 +20,59 @@ PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" els
 SEED_DEV = None  # optional uint64 device counter added to every dropout seed (set by the trainer for CUDA-graph replay)
 WGRAD_STREAM = None   # optional side stream: weight-gradient GEMMs run there, concurrently with the data-gradient chain (join_wgrad)
 _WGRAD_KEEP = []      # operands of in-flight side-stream launches (kept allocated until the join)
+PACK_CACHE = None   # optional PackCache: re-tiled tensor-core weight operands kept across calls (owner refreshes them after every weight update)
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
 PRO_NONE, PRO_LN, PRO_SWISH_DROP, PRO_BN_SWISH, PRO_DROP, PRO_IN_PRELU = range(6)
 EPI_NONE, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_DBNSWISH, EPI_ACC, EPI_SWISH_DUAL = range(6)
 
 Ptr = Union[None, torch.Tensor, Tuple[torch.Tensor, int]]
+
+
+class PackCache:
+    """Re-tiled (K-major, SWIZZLE_128B, tf32-rounded) copies of the weights the tensor-core GEMMs consume, keyed by the weight's
+    address + layout.  The first GEMM that meets a weight re-tiles it into a cached buffer; later launches skip that kernel
+    (``CmganGemmArgs.b_packed``).  The owner of the weights calls ``refresh()`` after changing them (one ``cmgan_pack_weights``
+    launch over a device table of all cached entries: FusedTrainer does so right after AdamW, inside the CUDA graph)."""
+
+    def __init__(self):
+        self.entries = {}      # key -> packed tensor
+        self.descs = []        # rows of the descriptor table (src, dst, sb_tap, sb_k, sb_n, Cin, ntaps, N)
+        self.table = None
+
+    def lookup(self, W: "Ptr", sb_tap: int, sb_k: int, sb_n: int, Cin: int, ntaps: int, N: int, dev):
+        """-> (packed tensor, True): the cached re-tiled copy of this weight (created and filled on first sight)"""
+        src = ptr(W)
+        key = (src, sb_tap, sb_k, sb_n, Cin, ntaps, N)
+        t = self.entries.get(key)
+        if t is not None:
+            return t, True
+        global LAUNCHES
+        t = torch.empty(N * Cin * ntaps, dtype=torch.float32, device=dev)
+        self.entries[key] = t
+        row = (src, t.data_ptr(), sb_tap, sb_k, sb_n, Cin, ntaps, N)
+        self.descs.append(row)
+        self.table = None
+        one = torch.tensor([row], dtype=torch.int64).to(dev)          # first sight (warm-up, never inside a graph capture): re-tile now
+        lib().call("cmgan_pack_weights", one.data_ptr(), 1, stream())
+        one.record_stream(torch.cuda.current_stream())
+        LAUNCHES += 1
+        return t, True
+
+    def refresh(self) -> None:
+        global LAUNCHES
+        if not self.descs:
+            return
+        if self.table is None:
+            dev = next(iter(self.entries.values())).device
+            self.table = torch.tensor(self.descs, dtype=torch.int64).to(dev)
+        lib().call("cmgan_pack_weights", self.table.data_ptr(), len(self.descs), stream())
+        LAUNCHES += 1
+
+    def clear(self) -> None:
+        self.entries.clear()
+        self.descs.clear()
+        self.table = None
 
 
 def ptr(t: Ptr) -> Optional[int]:
@@ -116,9 +163,15 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
     a.seed_dev = ptr(SEED_DEV)
     a.precision = PRECISION if precision is None else precision
     ws = None
+    packed = False
     if a.precision == 1 and not wgrad and N % 16 == 0 and N <= 256 and Cin % 32 == 0:
-        ws = torch.empty(N * Cin * ntaps, dtype=torch.float32, device=(A[0] if isinstance(A, tuple) else A).device)
+        dev = (A[0] if isinstance(A, tuple) else A).device
+        if PACK_CACHE is not None:
+            ws, packed = PACK_CACHE.lookup(W, sb_tap, sb_k, sb_n, Cin, ntaps, N, dev)
+        else:
+            ws = torch.empty(N * Cin * ntaps, dtype=torch.float32, device=dev)
         a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
+        a.b_packed = 1 if packed else 0
     global LAUNCHES
     name = "cmgan_gemm_wgrad_f32" if wgrad else "cmgan_gemm_rows_f32"
     if wgrad and WGRAD_STREAM is not None and PROBE is None:
@@ -141,4 +194,4 @@ def gemm(*, A: Ptr, lda: int, W: Ptr, sb_k: int, sb_n: int, C: Ptr, ldc: int, M:
             nbytes = 4 * (M * Cin + M * N * (1 + extra) + N * Cin * ntaps)
         keep = (A, W, C, bias, R, aux, e0, e1, D, dbias, C2, p0, p1, p2, ws)      # the operands stay allocated for the replay
         PROBE.append((name, M, N, Cin * ntaps, nbytes, a, keep))
-    LAUNCHES += 2 if ws is not None else 1
+    LAUNCHES += 2 if (ws is not None and not packed) else 1

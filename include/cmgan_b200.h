@@ -25,6 +25,7 @@ int cmgan_gemm_args_size(void);
 /* ---- dense contractions (replace nn.Linear / nn.Conv1d(k=1) / nn.Conv2d and their autograd; gemm_args.h) */
 int cmgan_gemm_rows_f32(const CmganGemmArgs* a, void* stream);
 int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream);
+int cmgan_pack_weights(const CmganPackDesc* descs, int n, void* stream);
 
 /* ---- LayerNorm (conformer.py:68,161,214), InstanceNorm2d (generator.py:35,55,61,128,148), BatchNorm1d (conformer.py:169) */
 int cmgan_ln_stats(const float* x, long long ldx, long long M, float* stats, void* stream);
@@ -73,7 +74,7 @@ int cmgan_recombine_bwd(const float* m1, const float* in_scale, const float* in_
 int cmgan_dropout_mask(float* out, long long n, unsigned long long seed, unsigned int thr, void* stream);
 int cmgan_stack2(const float* x, long long xb, long long xh, long long xw, const float* y, long long yb, long long yh, long long yw, int B, int H, int W, float* out, void* stream);
 int cmgan_unstack2(const float* dxy, long long n, float* dx, float* dy, void* stream);
-int cmgan_spectral_norm(const float* W, int R, int Cc, float* u, float* v, int training, float* w_sn, float* sigma, void* stream);
+int cmgan_spectral_norm(const float* W, int R, int Cc, float* u, float* v, int training, float* w_sn, float* sigma, float* uv_out, void* stream);
 int cmgan_spectral_norm_bwd(const float* w_sn, const float* dw_sn, int R, int Cc, const float* u, const float* v, const float* sigma, float* dW, void* stream);
 int cmgan_norm_maxpool(const float* x, int B, long long rows, int C, const float* scale, const float* shift, const float* slope, float* out, int* arg, void* stream);
 int cmgan_maxpool_bwd(const float* dout, const int* arg, int B, long long rows, int C, float* dact, void* stream);
@@ -88,7 +89,7 @@ int cmgan_time_loss(const float* ea, long long lde, const float* clean, long lon
 int cmgan_gen_loss_finalize(const double* acc, double n_spec, double n_time, float w_ri, float w_mag, float w_t, float w_gan, const float* fake, int B, float* loss, float* d_fake, void* stream);
 int cmgan_disc_loss(const float* d_max, const float* d_enh, const float* target, int B, float* loss, float* g_max, float* g_enh, void* stream);
 int cmgan_mag_bwd_add(const float* er, const float* ei, const float* d_mag, long long gb, long long gt, long long gf, int B, int T, int F, float* d_er, float* d_ei, void* stream);
-int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd, int step, const unsigned long long* step_dev, void* stream);
+int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd, int step, const unsigned long long* step_dev, const float* lr_dev, void* stream);
 int cmgan_counter_add(unsigned long long* p, unsigned long long v, void* stream);
 
 #ifdef __cplusplus

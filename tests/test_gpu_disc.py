@@ -77,3 +77,40 @@ def test_disc_backward_with_dropout(golden, d_weights):
         err = (p.grad.double().cpu() - ref_g).abs().max().item() / max(ref_g.abs().max().item(), 1e-3 * gmax)
         print(f"[parity] D grad {k}: rel {err:.3e}")
         assert err < 2e-3, k
+
+
+def test_two_train_forwards_then_backward_use_their_own_uv(d_weights, golden):
+    """discriminator step order (train.py:162-170): forward(clean, est), forward(clean, clean) -- a second power iteration -- then
+    the backward of both.  torch's spectral_norm keeps the (u, v) of each forward for its own backward; so must this path."""
+    import cmgan_b200.discriminator as D
+    x = torch.from_numpy(golden["d_x"])
+    y = torch.from_numpy(golden["d_y"])
+    m = _model(d_weights).train()
+    old, D.DROP_P = D.DROP_P, 0.0
+    try:
+        P = m._tensor_dict()
+        G = {k: torch.zeros_like(v) for k, v in m.named_parameters()}
+        s1, s2 = {}, {}
+        o1 = D.disc_fwd(x.to(DEV), y.to(DEV), P, True, 1, s1)
+        o2 = D.disc_fwd(x.to(DEV), x.to(DEV), P, True, 2, s2)
+        g1, g2 = torch.tensor([[0.7], [-0.3]], device=DEV), torch.tensor([[0.2], [0.5]], device=DEV)
+        D.disc_bwd(s1, g1, P, G, False, False)
+        D.disc_bwd(s2, g2, P, G, False, False)
+    finally:
+        D.DROP_P = old
+    sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() and not k.endswith(("_u", "_v")) else v.double() if v.is_floating_point() else v)
+          for k, v in d_weights.items()}
+    uv = {}
+    r1 = O.discriminator_forward(x.double(), y.double(), sd, training=True, uv_out=uv)
+    sd2 = dict(sd)
+    for li, (u, v) in uv.items():
+        sd2[f"layers.{li}.weight_u"], sd2[f"layers.{li}.weight_v"] = u, v
+    r2 = O.discriminator_forward(x.double(), x.double(), sd2, training=True)
+    ((r1 * g1.cpu().double()).sum() + (r2 * g2.cpu().double()).sum()).backward()
+    _chk(o1, r1, 1e-5, "first train forward")
+    _chk(o2, r2, 1e-5, "second train forward (second power iteration)")
+    gmax = max(v.grad.abs().max().item() for v in sd.values() if getattr(v, "grad", None) is not None)
+    for k in G:
+        err = (G[k].double().cpu() - sd[k].grad).abs().max().item() / max(sd[k].grad.abs().max().item(), 1e-3 * gmax)
+        print(f"[parity] D two-forward grad {k}: rel {err:.3e}")
+        assert err < 2e-3, k

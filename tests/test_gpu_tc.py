@@ -194,4 +194,6 @@ def test_tc_training_gradients(g_weights, golden):
         if e > worst:
             worst, wk = e, k
     print(f"[parity-tf32] worst relative parameter-gradient deviation tf32 vs fp32: {worst:.3e} at {wk}")
-    assert worst < 0.15      # tf32 operand rounding amplified by the InstanceNorm / LayerNorm cancellations of a 60-layer backward pass (fp32 itself: 3e-3)
+    # tf32 operand rounding (2^-11 per operand) amplified by the InstanceNorm / LayerNorm cancellations of a 60-layer backward pass; measured 6e-2 at
+    # complex_decoder.dense_block.conv2.weight.  tests/test_gpu_trainmode.py holds the same path against the float64 oracle (whole network and per kernel).
+    assert worst < 0.08

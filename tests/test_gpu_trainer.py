@@ -72,7 +72,7 @@ def test_adamw_kernel_matches_torch():
         g = torch.randn(10007, device=DEV)
         ref.grad = g.clone()
         opt.step()
-        call("cmgan_adamw", p, g, m, v, p.numel(), 5e-4, 0.9, 0.999, 1e-8, 0.01, step, None)
+        call("cmgan_adamw", p, g, m, v, p.numel(), 5e-4, 0.9, 0.999, 1e-8, 0.01, step, None, None)
     err = (p - ref.detach()).abs().max().item()
     print(f"[parity] AdamW 3 steps max-abs {err:.3e}")
     assert err < 1e-6
@@ -92,3 +92,58 @@ def test_training_makes_progress(g_weights, d_weights, golden):
         assert np.isfinite(dl)
     print("[train] generator losses:", [f"{x:.4f}" for x in losses])
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_lr_schedule_under_graph_replay_and_checkpoint_roundtrip(g_weights, d_weights, golden, tmp_path):
+    """StepLR (train.py:248-253) must act on a CAPTURED step (lr is a device scalar), capturing must not consume training steps or
+    touch BatchNorm / spectral-norm buffers, and save -> load -> step must continue bit-exactly (train.py:273, evaluation.py:64)."""
+    clean = torch.from_numpy(golden["grad_clean"]).to(DEV)
+    noisy = torch.from_numpy(golden["grad_noisy"]).to(DEV)
+    m, d = _models(g_weights, d_weights)
+    m.train(); d.train()
+    t = FusedTrainer(m, d, lr=1e-3, decay_epoch=1)
+    bufs0 = {k: v.clone() for k, v in list(m.named_buffers()) + [("D." + k, v) for k, v in d.named_buffers()]}
+    p0 = t.pg.clone()
+    t.capture_train_step(clean, noisy)
+    assert torch.equal(t.pg, p0), "capture must not update the parameters"
+    for k, v in list(m.named_buffers()) + [("D." + k, v) for k, v in d.named_buffers()]:
+        assert torch.equal(v, bufs0[k]), f"capture changed buffer {k}"
+    assert t.opt_g.t == 0 and int(t.opt_g.t_dev.item()) == 0 and int(t.step_dev.item()) == 0
+    pesq_t = torch.tensor([0.4, 0.6], device=DEV)
+    lg, ld = t.replay_train_step(clean, noisy, pesq_t)
+    assert np.isfinite(lg.item()) and np.isfinite(ld.item())
+    step1 = (t.pg - p0).abs().max().item()
+    assert step1 > 0 and int(t.opt_g.t_dev.item()) == 1
+    # a full checkpoint, then two more replays under a halved learning rate
+    ck = str(tmp_path / "ckpt_full")
+    t.save_checkpoint(ck, full=True)
+    ref_ck = str(tmp_path / "ckpt_ref_format")
+    t.save_checkpoint(ref_ck)
+    t.scheduler_step()            # decay_epoch = 1: lr 1e-3 -> 5e-4, D 2e-3 -> 1e-3
+    assert abs(t.opt_g.lr - 5e-4) < 1e-12 and abs(t.opt_d.lr - 1e-3) < 1e-12
+    p1 = t.pg.clone()
+    t.replay_train_step(clean, noisy, pesq_t)
+    p2 = t.pg.clone()
+    # Adam's first steps move every weight by ~lr: the captured graph must follow the new device-side lr
+    ratio = (p2 - p1).abs().mean().item() / (p1 - p0).abs().mean().item()
+    print(f"[lr] mean |update| after halving lr / before: {ratio:.3f}")
+    assert 0.3 < ratio < 0.7
+    # resume from the checkpoint in a fresh trainer: same lr schedule position, same next step
+    m2, d2 = _models(g_weights, d_weights)
+    m2.train(); d2.train()
+    t2 = FusedTrainer(m2, d2, lr=1e-3, decay_epoch=1)
+    t2.load_checkpoint(ck)
+    assert torch.equal(t2.pg, p1)
+    t2.scheduler_step()
+    t2.generator_step(clean, noisy)
+    t2.discriminator_step(pesq_t)
+    # same dropout masks (device counter), same statistics; atomics reorder the gradient sums, and AdamW turns a noise-level gradient
+    # (conv biases in front of an InstanceNorm: mathematically zero) into a +-lr step, so compare robustly
+    diff = (t2.pg - p2).abs()
+    print(f"[ckpt] resumed eager step vs original graph replay: parameter difference median {diff.median().item():.3e}, "
+          f"99.9th percentile {diff.float().quantile(0.999).item():.3e}, max {diff.max().item():.3e}")
+    assert diff.median().item() <= 1e-6 and (diff > 1e-4).float().mean().item() < 0.01
+    # the reference-format file is a plain state dict with the reference's 359 keys: strict load into a fresh module
+    sd = torch.load(ref_ck, map_location="cpu")
+    assert len(sd) == 359
+    cmgan_b200.TSCNet(64, 201).load_state_dict(sd, strict=True)
