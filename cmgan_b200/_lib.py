@@ -85,6 +85,8 @@ class _Lib:
             fn = getattr(self.cdll, name)      # AttributeError if the library lacks a declared symbol
             fn.restype = ret
             fn.argtypes = [t for t, _ in argl]
+        # the library-wide tf32 operand-rounding mode starts in step with ops.PRECISION's default (ops.set_precision keeps it so)
+        self.cdll.cmgan_set_tf32_rounding(1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" else 0)
         if self.cdll.cmgan_gemm_args_size() != ctypes.sizeof(GemmArgs):
             raise RuntimeError("GemmArgs layout mismatch between _lib.py and gemm_args.h "
                                f"({ctypes.sizeof(GemmArgs)} vs {self.cdll.cmgan_gemm_args_size()})")

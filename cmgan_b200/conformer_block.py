@@ -72,11 +72,14 @@ def _inst_norm_site(x, ldx, G, rows, Cn, gamma, beta, tabs: _Tabs, c0, slope_w, 
         call("cmgan_copy_rows", slope_w, Cn, (tabs.slope, c0), Cn, 1, Cn)
 
 
-def _norm_bwd(x, ldx, dact, ldd, G, rows, Cn, act, batch_stats, tabs: _Tabs, c0, slope, dx, lddx, dgamma, dbeta, dslope, sums: _Sums):
+def _norm_bwd(x, ldx, dact, ldd, G, rows, Cn, act, batch_stats, tabs: _Tabs, c0, slope, dx, lddx, dgamma, dbeta, dslope, sums: _Sums,
+              operand: bool = False):
+    """``operand``: dx is read by tensor-core contractions (data + weight gradient of a convolution): rounded to tf32 on store in tf32 mode"""
     s = sums.take(G * Cn * 2)
     args = ((tabs.scale, c0), (tabs.shift, c0), (tabs.mean, c0), (tabs.rstd, c0), tabs.width, slope)
     call("cmgan_norm_bwd_reduce", x, ldx, dact, ldd, G, rows, Cn, act, *args, s, dslope)
-    call("cmgan_norm_bwd_apply", x, ldx, dact, ldd, G, rows, Cn, act, 1 if batch_stats else 0, *args, s, dx, lddx, dgamma, dbeta)
+    call("cmgan_norm_bwd_apply", x, ldx, dact, ldd, G, rows, Cn, act | (16 if operand and ops.PRECISION == 1 else 0), 1 if batch_stats else 0, *args, s,
+         dx, lddx, dgamma, dbeta)
 
 
 def _site_seed(seed: int, block_id: int, site: int) -> int:
@@ -107,6 +110,16 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
 
     def ff(xin, name, s1, s2):
         """0.5 * FF(LN(x)) + x  (ref: conformer.py:54-72,136-148,211-212)"""
+        if ops.PRECISION == 1 and ops.FUSED_FFN and not keep:
+            # one kernel: the (M, 256) hidden activation lives in TMEM / shared memory only (csrc/ffn_fused.cu)
+            W1, W2 = P[f"{p}.{name}.fn.fn.net.0.weight"], P[f"{p}.{name}.fn.fn.net.3.weight"]
+            out = _empty(M, C, dev=dev)
+            thr, inv = ops.drop_params(dp)
+            call("cmgan_ffn_fwd", xin, C, M, P[f"{p}.{name}.fn.norm.weight"], P[f"{p}.{name}.fn.norm.bias"],
+                 ops.packed_weight(W1, 0, 1, C, C, 1, 4 * C), P[f"{p}.{name}.fn.fn.net.0.bias"],
+                 ops.packed_weight(W2, 0, 1, 4 * C, 4 * C, 1, C), P[f"{p}.{name}.fn.fn.net.3.bias"], 0.5,
+                 s1 & 0xFFFFFFFFFFFFFFFF, s2 & 0xFFFFFFFFFFFFFFFF, thr, inv, ops.SEED_DEV, out, C)
+            return None, out
         xn, st = layer_norm(xin, f"{p}.{name}.fn.norm.weight", f"{p}.{name}.fn.norm.bias")
         h = _empty(M, 4 * C, dev=dev) if keep else None          # pre-activation: only the backward pass needs it
         a = _empty(M, 4 * C, dev=dev)                            # swish(h) * dropout: operand of the second Linear

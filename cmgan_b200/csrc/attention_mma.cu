@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
         const long row = base + (long)i * g.tok_stride;
 #pragma unroll
         for (int nd = 0; nd < 2; ++nd)
-            *reinterpret_cast<float2*>(ctx + row * CQ + h * D + nd * 8 + 2 * t) = make_float2(o[nd][hrow * 2] * inv, o[nd][hrow * 2 + 1] * inv);
+            *reinterpret_cast<float2*>(ctx + row * CQ + h * D + nd * 8 + 2 * t) = make_float2(tf32r(o[nd][hrow * 2] * inv), tf32r(o[nd][hrow * 2 + 1] * inv));
         if (lse && t == 0) lse[row * H + h] = mrun[hrow] + log2f(lrun[hrow]);
     }
 }
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
 #pragma unroll
                 for (int nd = 0; nd < 2; ++nd)
                     *reinterpret_cast<float2*>(dqkv + row * LDQ + h * D + nd * 8 + 2 * t) =
-                        make_float2(0.25f * dq[nd][hrow * 2], 0.25f * dq[nd][hrow * 2 + 1]);
+                        make_float2(tf32r(0.25f * dq[nd][hrow * 2]), tf32r(0.25f * dq[nd][hrow * 2 + 1]));       // dqkv feeds two tensor-core contractions
             }
         }
     }
@@ -610,8 +610,8 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dkv_mma_kernel(const float* _
         float* p = dqkv + (base + (long)j * g.tok_stride) * LDQ + h * D + 2 * t;
 #pragma unroll
         for (int nd = 0; nd < 2; ++nd) {
-            *reinterpret_cast<float2*>(p + CQ + nd * 8) = make_float2(0.25f * dk[nd][hrow * 2], 0.25f * dk[nd][hrow * 2 + 1]);      // Q was staged unscaled
-            *reinterpret_cast<float2*>(p + 2 * CQ + nd * 8) = make_float2(dv[nd][hrow * 2], dv[nd][hrow * 2 + 1]);
+            *reinterpret_cast<float2*>(p + CQ + nd * 8) = make_float2(tf32r(0.25f * dk[nd][hrow * 2]), tf32r(0.25f * dk[nd][hrow * 2 + 1]));      // Q was staged unscaled
+            *reinterpret_cast<float2*>(p + 2 * CQ + nd * 8) = make_float2(tf32r(dv[nd][hrow * 2]), tf32r(dv[nd][hrow * 2 + 1]));
         }
     }
 }

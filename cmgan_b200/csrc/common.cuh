@@ -21,6 +21,18 @@ int cmgan_check_launch(const char* what);   // cudaGetLastError() -> 0 / -1 (+ m
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- tf32 operand rounding -----------------------------------------------------------------------------
+// The tensor cores read fp32 operands and IGNORE the low 13 mantissa bits (truncation, a bias towards zero).  In tf32 mode every kernel
+// that writes a tensor a tensor-core contraction will read therefore rounds it to nearest (cvt.rna.tf32.f32) on store.  The mode is
+// library-wide (cmgan_set_tf32_rounding; cmgan_b200.ops.set_precision keeps it in step with the GEMM precision).
+extern int g_cmgan_round_tf32;
+__device__ __forceinline__ float cmgan_rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float cmgan_maybe_rna(float x, int on) { return on ? cmgan_rna_tf32(x) : x; }
+
 // ---- math ----------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }

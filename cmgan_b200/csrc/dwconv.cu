@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __rest
 // backward.  dz = grad wrt out (M, 128).  dg (M, 256) overwritten; dw (128, 31), dbias (128) accumulated.
 __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ dz, SeqGeom sg,
                                                              const float* __restrict__ w, int seqs_per_block, float* __restrict__ dg,
-                                                             float* __restrict__ dw, float* __restrict__ dbias) {
+                                                             float* __restrict__ dw, float* __restrict__ dbias, int rnd) {
     extern __shared__ __align__(16) float smem[];
     float* U = smem;                    // [ROWS][CH]
     float* DZ = smem + ROWS * CH;       // [ROWS][CH]
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __rest
                     const long row = base + (long)tok * sg.tok_stride;
                     const float sg_ = SG[(tl + i) * CH + c];
                     const float u = U[(tl + i + PADL) * CH + c];            // a * sigmoid(b)
-                    dg[row * (2 * CH) + c] = du[i] * sg_;
-                    dg[row * (2 * CH) + CH + c] = du[i] * u * (1.f - sg_);
+                    dg[row * (2 * CH) + c] = cmgan_maybe_rna(du[i] * sg_, rnd);                    // dg feeds two tensor-core contractions
+                    dg[row * (2 * CH) + CH + c] = cmgan_maybe_rna(du[i] * u * (1.f - sg_), rnd);
                 }
             }
         }
@@ -160,6 +160,6 @@ CMGAN_API int cmgan_glu_dwconv_bwd(const float* g, const float* dz, const float*
     // enough blocks for ~4 waves of 148 SMs x 2 resident blocks, but at least one sequence per block
     int spb = sg.n_seq / (148 * 2 * 4);
     if (spb < 1) spb = 1;
-    glu_dwconv_bwd_kernel<<<cdiv(sg.n_seq, spb), 256, smem, (cudaStream_t)stream>>>(g, dz, sg, w, spb, dg, dw, dbias);
+    glu_dwconv_bwd_kernel<<<cdiv(sg.n_seq, spb), 256, smem, (cudaStream_t)stream>>>(g, dz, sg, w, spb, dg, dw, dbias, g_cmgan_round_tf32);
     return cmgan_check_launch("glu_dwconv_bwd_kernel");
 }

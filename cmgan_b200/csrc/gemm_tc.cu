@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                             if (EPI == CMGAN_EPI_SWISH_DUAL) {
                                 if (cptr) *reinterpret_cast<float4*>(cptr + rd * ldc) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) v[j] = swishf_(v[j]) * ds[j];
+                                for (int j = 0; j < 4; ++j) v[j] = to_tf32(swishf_(v[j]) * ds[j]);      // operand of the next contraction: round, the tensor core would truncate
                                 *reinterpret_cast<float4*>(c2ptr + rd * ldc2) = make_float4(v[0], v[1], v[2], v[3]);
                                 continue;
                             }
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(EPI8 ? NTHREADS8 : NTHREADS4, (ASYNC_A && !EPI
                                 for (int j = 0; j < 4; ++j) v[j] = alpha * v[j] * ds[j] + (xbase ? x[j] : 0.f);
                             } else if (EPI == CMGAN_EPI_DSWISH_DROP) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) v[j] = v[j] * dswishf_(x[j]) * ds[j];
+                                for (int j = 0; j < 4; ++j) v[j] = to_tf32(v[j] * dswishf_(x[j]) * ds[j]);   // feeds the next data-gradient GEMM and a weight-gradient GEMM
                             } else if (EPI == CMGAN_EPI_DBNSWISH) {
                                 const float sa[4] = {e0v.x, e0v.y, e0v.z, e0v.w}, sb[4] = {e1v.x, e1v.y, e1v.z, e1v.w};
 #pragma unroll

@@ -7,6 +7,9 @@
 
 static thread_local char g_err[512] = "";
 
+int g_cmgan_round_tf32 = 0;
+CMGAN_API int cmgan_set_tf32_rounding(int on) { g_cmgan_round_tf32 = on ? 1 : 0; return 0; }
+
 void cmgan_set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -56,7 +56,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const flo
                               float* __restrict__ dx, long lddx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp,
                               float* __restrict__ dz, long lddz, float zalpha, unsigned long long zseed, unsigned zthr, float zinv_keep,
-                              const unsigned long long* __restrict__ seed_dev) {
+                              const unsigned long long* __restrict__ seed_dev, int rnd) {
     __shared__ float sg[8][LN_C], sb[8][LN_C];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     long r0 = ((long)blockIdx.x * nw + warp) * rows_per_warp;
@@ -87,7 +87,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const flo
                 s0 = (h & 0xFFFFu) >= zt16 ? zalpha * zinv_keep : 0.f;
                 s1 = (h >> 16) >= zt16 ? zalpha * zinv_keep : 0.f;
             }
-            reinterpret_cast<float2*>(dz + row * lddz)[lane] = make_float2(o.x * s0, o.y * s1);
+            reinterpret_cast<float2*>(dz + row * lddz)[lane] = make_float2(cmgan_maybe_rna(o.x * s0, rnd), cmgan_maybe_rna(o.y * s1, rnd));
         }
         ag.x += d.x * xh0; ag.y += d.y * xh1; ab.x += d.x; ab.y += d.y;
     }
@@ -282,7 +282,7 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, con
                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                       const float* __restrict__ mean, const float* __restrict__ rstd, long tstride,
                                       const float* __restrict__ slope, const double* __restrict__ S,
-                                      float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                      float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rnd) {
     const int grp = blockIdx.y;
     const long r_beg = (long)blockIdx.x * chunk;
     const long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
@@ -300,7 +300,7 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, long ldx, con
         const float v = __ldg(x + (rb + r) * ldx + c), d = __ldg(dact + (rb + r) * ldd + c);
         const float z = v * sc + sh;
         const float gq = (act && z < 0.f) ? d * a : d;
-        dx[(rb + r) * lddx + c] = sc * (gq - m1 - (v - mu) * rs * m2);
+        dx[(rb + r) * lddx + c] = cmgan_maybe_rna(sc * (gq - m1 - (v - mu) * rs * m2), rnd);
     }
 }
 
@@ -310,7 +310,7 @@ __global__ void norm_bwd_apply4_kernel(const float* __restrict__ x, long ldx, co
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        const float* __restrict__ mean, const float* __restrict__ rstd, long tstride,
                                        const float* __restrict__ slope, const double* __restrict__ S,
-                                       float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                       float* __restrict__ dx, long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rnd) {
     const int grp = blockIdx.y, cv = C / 4;
     const long r_beg = (long)blockIdx.x * chunk;
     const long r_end = r_beg + chunk < rows_per_group ? r_beg + chunk : rows_per_group;
@@ -343,7 +343,7 @@ __global__ void norm_bwd_apply4_kernel(const float* __restrict__ x, long ldx, co
         for (int j = 0; j < 4; ++j) {
             const float z = fmaf(v[j], sc[j], sh[j]);
             const float gq = (act && z < 0.f) ? d[j] * a[j] : d[j];
-            o[j] = sc[j] * (gq - m1[j] - (v[j] - mu[j]) * rs[j] * m2[j]);
+            o[j] = cmgan_maybe_rna(sc[j] * (gq - m1[j] - (v[j] - mu[j]) * rs[j] * m2[j]), rnd);
         }
         *reinterpret_cast<float4*>(dx + (rb + r) * lddx + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -393,12 +393,14 @@ __global__ void fill_kernel(float* p, long n, float v) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void copy_rows_kernel(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, long M, int C) {
+__global__ void copy_rows_kernel(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, long M, int C, int rnd) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = M * (C / 4);
     if (i >= total) return;
     long row = i / (C / 4); int c4 = (int)(i % (C / 4));
-    reinterpret_cast<float4*>(dst + row * ldd)[c4] = __ldg(reinterpret_cast<const float4*>(src + row * lds) + c4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(src + row * lds) + c4);
+    if (rnd) v = make_float4(cmgan_rna_tf32(v.x), cmgan_rna_tf32(v.y), cmgan_rna_tf32(v.z), cmgan_rna_tf32(v.w));
+    reinterpret_cast<float4*>(dst + row * ldd)[c4] = v;
 }
 
 __global__ void add_rows_kernel(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, long M, int C) {
@@ -441,7 +443,7 @@ static int ln_bwd_launch(const float* dy, long long lddy, const float* x, long l
     const int rpw = 16;
     ln_bwd_kernel<<<cdiv(M, 8 * rpw), 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, reinterpret_cast<const float2*>(stats), gamma, M, res, ldr,
                                                                      res2, ldr2, dx, lddx, dgamma, dbeta, rpw, dz, lddz, zalpha, zseed, zthr,
-                                                                     zinv_keep, seed_dev);
+                                                                     zinv_keep, seed_dev, g_cmgan_round_tf32);
     return cmgan_check_launch("ln_bwd_kernel");
 }
 
@@ -498,6 +500,7 @@ CMGAN_API int cmgan_norm_bwd_reduce(const float* x, long long ldx, const float* 
                                     int C, int act, const float* scale, const float* shift, const float* mean, const float* rstd,
                                     long long tstride, const float* slope, double* S, float* dslope, void* stream) {
     CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S, "cmgan_norm_bwd_reduce: null pointer");
+    act &= 15;          // bit 4 is the tf32-rounding request of cmgan_norm_bwd_apply
     CMGAN_REQUIRE(C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_bwd_reduce: C=%d unsupported", C);
     if (G == 0 || rows_per_group == 0) return 0;
     if (C % 4 == 0 && ldx % 4 == 0 && ldd % 4 == 0 && tstride % 4 == 0 &&
@@ -522,6 +525,8 @@ CMGAN_API int cmgan_norm_bwd_apply(const float* x, long long ldx, const float* d
                                    const float* rstd, long long tstride, const float* slope, const double* S, float* dx,
                                    long long lddx, float* dgamma, float* dbeta, void* stream) {
     CMGAN_REQUIRE(x && dact && scale && shift && mean && rstd && S && dx, "cmgan_norm_bwd_apply: null pointer");
+    const int rnd = (act >> 4) & 1;       // act | 16: dx feeds tensor-core contractions, round it to tf32 (nearest) on store
+    act &= 15;
     CMGAN_REQUIRE(C >= 1 && C <= 256 && 256 % C == 0, "cmgan_norm_bwd_apply: C=%d unsupported", C);
     if (G == 0 || rows_per_group == 0) return 0;
     if (C % 4 == 0 && ldx % 4 == 0 && ldd % 4 == 0 && lddx % 4 == 0 && tstride % 4 == 0 &&
@@ -531,14 +536,14 @@ CMGAN_API int cmgan_norm_bwd_apply(const float* x, long long ldx, const float* d
         const int chunk4 = nrg4 * 16;
         dim3 grid4(cdiv(rows_per_group, chunk4), G);
         norm_bwd_apply4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, C, chunk4, act, use_batch_stats, scale, shift,
-                                                                       mean, rstd, tstride, slope, S, dx, lddx, dgamma, dbeta);
+                                                                       mean, rstd, tstride, slope, S, dx, lddx, dgamma, dbeta, rnd);
         return cmgan_check_launch("norm_bwd_apply4_kernel");
     }
     const int nrg = 256 / C;
     const int chunk = nrg * 32;
     dim3 grid(cdiv(rows_per_group, chunk), G);
     norm_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, dact, ldd, rows_per_group, C, chunk, act, use_batch_stats, scale, shift,
-                                                                 mean, rstd, tstride, slope, S, dx, lddx, dgamma, dbeta);
+                                                                 mean, rstd, tstride, slope, S, dx, lddx, dgamma, dbeta, rnd);
     return cmgan_check_launch("norm_bwd_apply_kernel");
 }
 
@@ -563,7 +568,17 @@ CMGAN_API int cmgan_fill(float* p, long long n, float v, void* stream) {
 CMGAN_API int cmgan_copy_rows(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream) {
     CMGAN_REQUIRE(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cmgan_copy_rows: bad arguments");
     if (M == 0) return 0;
-    copy_rows_kernel<<<cdiv(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, M, C);
+    copy_rows_kernel<<<cdiv(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, M, C, 0);
+    return cmgan_check_launch("copy_rows_kernel");
+}
+
+// same copy with every element rounded to tf32 (nearest) when the library is in tf32 mode: the destination is the operand of a tensor-core
+// contraction (src == dst rounds in place)
+CMGAN_API int cmgan_copy_rows_operand(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream) {
+    CMGAN_REQUIRE(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cmgan_copy_rows_operand: bad arguments");
+    if (M == 0) return 0;
+    if (src == dst && !g_cmgan_round_tf32) return 0;
+    copy_rows_kernel<<<cdiv(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, M, C, g_cmgan_round_tf32);
     return cmgan_check_launch("copy_rows_kernel");
 }
 

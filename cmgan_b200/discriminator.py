@@ -76,7 +76,7 @@ def _disc_fwd(x, y, P, training: bool, seed: int, save):
         layers.append(dict(a_in=act, Cin=Cin, ih=ih, iw=iw, oh=oh, ow=ow, Cout=Cout, raw=raw, tab=tab, w_sn=w_sn, sigma=sigma, key=key, idx=idx))
         if li < 3:
             nxt = _empty(M, Cout, dev=dev)
-            call("cmgan_norm_apply", raw, Cout, B, oh * ow, Cout, 1, tab.scale, tab.shift, Cout, slope, nxt, Cout)
+            call("cmgan_norm_apply", raw, Cout, B, oh * ow, Cout, 1 | (16 if ops.PRECISION == 1 else 0), tab.scale, tab.shift, Cout, slope, nxt, Cout)
             act, Cin, ih, iw = nxt, Cout, oh, ow
         else:
             pooled = _empty(B, Cout, dev=dev)
@@ -166,7 +166,7 @@ def _disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
             call("cmgan_maxpool_bwd", dpool, S["arg"], B, oh * ow, Cout, dact)
         draw = _empty(M, Cout, dev=dev)
         _norm_bwd(L["raw"], Cout, dact, Cout, B, oh * ow, Cout, 1, True, L["tab"], 0, P[f"layers.{idx + 2}.weight"], draw, Cout,
-                  G[f"layers.{idx + 1}.weight"], G[f"layers.{idx + 1}.bias"], G[f"layers.{idx + 2}.weight"], sums)
+                  G[f"layers.{idx + 1}.weight"], G[f"layers.{idx + 1}.bias"], G[f"layers.{idx + 2}.weight"], sums, operand=True)
         conv = dict(OH=oh, OW=ow, IH=ih, IW=iw, mul_y=2, mul_x=2)
         dw_sn = torch.zeros_like(L["w_sn"])
         gemm(wgrad=True, A=L["a_in"], lda=Cin, Cin=Cin, taps=_TAPS, conv=conv, D=draw, ldd=Cout, N=Cout, W=None, C=dw_sn, sb_tap=1, sb_k=16,

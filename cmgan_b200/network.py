@@ -61,7 +61,7 @@ def dense_block_bwd(cat, raws, tabs, dcat, P, G, p, B, T, Fw, sums: _Sums):
         dil, c0, Cin, co = 2 ** (i - 1), (5 - i) * C, C * i, (4 - i) * C
         draw = _empty(M, C, dev=dev)        # one per layer: the weight-gradient GEMM may still be reading it on the side stream
         _norm_bwd(raws[i - 1], C, (dcat, co), CAT, B, rows, C, 1, True, tabs[i - 1], 0, P[f"{p}.prelu{i}.weight"], draw, C,
-                  G[f"{p}.norm{i}.weight"], G[f"{p}.norm{i}.bias"], G[f"{p}.prelu{i}.weight"], sums)
+                  G[f"{p}.norm{i}.weight"], G[f"{p}.norm{i}.bias"], G[f"{p}.prelu{i}.weight"], sums, operand=True)
         taps = _dense_taps(dil)
         gemm(wgrad=True, A=(cat, c0), lda=CAT, Cin=Cin, taps=taps, conv=dict(OH=T, OW=Fw, IH=T, IW=Fw), D=draw, ldd=C, N=C, W=None,
              C=G[f"{p}.conv{i}.weight"], sb_tap=1, sb_k=6, sb_n=Cin * 6, ldc=0, M=M, dbias=G[f"{p}.conv{i}.bias"])
@@ -108,7 +108,7 @@ def tscnet_fwd(x, P, training: bool, seed: int, save: Optional[dict]):
     dec = {}
     for pd in ("mask_decoder", "complex_decoder"):
         cat = _empty(M2, CAT, dev=dev)
-        call("cmgan_copy_rows", h, C, (cat, 4 * C), CAT, M2, C)
+        call("cmgan_copy_rows_operand", h, C, (cat, 4 * C), CAT, M2, C)         # operand of the decoder's first convolution
         raws, tabs = dense_block_fwd(cat, P, pd + ".dense_block", B, T, F2, sums)
         sp = _empty(M2, 2 * C, dev=dev)      # == (B, T, 2*F2, 64): the sub-pixel shuffle is a free reinterpretation
         gemm(A=cat, lda=CAT, W=P[pd + ".sub_pixel.conv.weight"], sb_tap=1, sb_k=3, sb_n=3 * C, bias=P[pd + ".sub_pixel.conv.bias"], C=sp, ldc=2 * C,
@@ -166,12 +166,13 @@ def tscnet_bwd(S: dict, dfr, dfi, P, G: Dict[str, torch.Tensor], after_tscb=None
     dsp[pm] = _empty(M2, 2 * C, dev=dev)
     call("cmgan_rowdot_bwd", dec[pm]["sp"], B, T, F, 1, None, None, None, P[pm + ".conv_1.weight"], dm1, dsp[pm], G[pm + ".conv_1.weight"],
          G[pm + ".conv_1.bias"])
+    call("cmgan_copy_rows_operand", dsp[pm], 2 * C, dsp[pm], 2 * C, M2, 2 * C)      # operand of the sub-pixel convolution's gradient GEMMs
     dactc = _empty(M2, 2 * C, dev=dev)
     call("cmgan_rowdot_bwd", dec[pc]["sp"], B, T, F, 2, tabC.scale, tabC.shift, P[pc + ".prelu.weight"], P[pc + ".conv.weight"], dcplx, dactc,
          G[pc + ".conv.weight"], G[pc + ".conv.bias"])
     dsp[pc] = _empty(M2, 2 * C, dev=dev)
     _norm_bwd(dec[pc]["sp"], C, dactc, C, B, T * 2 * F2, C, 1, True, tabC, 0, P[pc + ".prelu.weight"], dsp[pc], C, G[pc + ".norm.weight"],
-              G[pc + ".norm.bias"], G[pc + ".prelu.weight"], sums)
+              G[pc + ".norm.bias"], G[pc + ".prelu.weight"], sums, operand=True)
     dh = None
     for pd in (pm, pc):
         cat = dec[pd]["cat"]
@@ -199,7 +200,7 @@ def tscnet_bwd(S: dict, dfr, dfi, P, G: Dict[str, torch.Tensor], after_tscb=None
     catE, tab2 = S["catE"], S["tab2"]
     de2 = _empty(M2, C, dev=dev)
     _norm_bwd(S["e2"], C, dh, C, B, T * F2, C, 1, True, tab2, 0, P[pe + ".conv_2.2.weight"], de2, C, G[pe + ".conv_2.1.weight"],
-              G[pe + ".conv_2.1.bias"], G[pe + ".conv_2.2.weight"], sums)
+              G[pe + ".conv_2.1.bias"], G[pe + ".conv_2.2.weight"], sums, operand=True)
     gemm(wgrad=True, A=catE, lda=CAT, Cin=C, taps=_W3, conv=dict(OH=T, OW=F2, IH=T, IW=F, mul_x=2), D=de2, ldd=C, N=C, W=None,
          C=G[pe + ".conv_2.0.weight"], sb_tap=1, sb_k=3, sb_n=3 * C, ldc=0, M=M2, dbias=G[pe + ".conv_2.0.bias"])
     dcatE = _empty(M, CAT, dev=dev)

@@ -20,6 +20,7 @@ PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" els
 SEED_DEV = None  # optional uint64 device counter added to every dropout seed (set by the trainer for CUDA-graph replay)
 WGRAD_STREAM = None   # optional side stream: weight-gradient GEMMs run there, concurrently with the data-gradient chain (join_wgrad)
 _WGRAD_KEEP = []      # operands of in-flight side-stream launches (kept allocated until the join)
+FUSED_FFN = os.environ.get("CMGAN_FUSED_FFN", "1") != "0"   # tf32 mode: one tcgen05 kernel per feed-forward module (csrc/ffn_fused.cu)
 PACK_CACHE = None   # optional PackCache: re-tiled tensor-core weight operands kept across calls (owner refreshes them after every weight update)
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
 
@@ -98,6 +99,13 @@ def call(name: str, *args) -> None:
     LAUNCHES += _KERNELS.get(name, 1)
 
 
+def packed_weight(W: "Ptr", sb_tap: int, sb_k: int, sb_n: int, Cin: int, ntaps: int, N: int) -> torch.Tensor:
+    """the re-tiled tensor-core image of a weight (see PackCache): from the active cache, or a one-off copy when none is active"""
+    dev = (W[0] if isinstance(W, tuple) else W).device
+    cache = PACK_CACHE if PACK_CACHE is not None else PackCache()
+    return cache.lookup(W, sb_tap, sb_k, sb_n, Cin, ntaps, N, dev)[0]
+
+
 def join_wgrad() -> None:
     """the current stream waits for every weight-gradient launch issued on the side stream (end of a backward pass)"""
     if WGRAD_STREAM is not None:
@@ -110,6 +118,7 @@ def set_precision(mode: str) -> None:
     global PRECISION
     assert mode in ("fp32", "tf32")
     PRECISION = 1 if mode == "tf32" else 0
+    lib().cdll.cmgan_set_tf32_rounding(PRECISION)      # producers of tensor-core operands round to nearest on store (the unit would truncate)
 
 
 def drop_params(p: float):

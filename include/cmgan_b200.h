@@ -21,11 +21,15 @@ extern "C" {
 const char* cmgan_last_error(void);
 int cmgan_abi_version(void);
 int cmgan_gemm_args_size(void);
+int cmgan_set_tf32_rounding(int on);
 
 /* ---- dense contractions (replace nn.Linear / nn.Conv1d(k=1) / nn.Conv2d and their autograd; gemm_args.h) */
 int cmgan_gemm_rows_f32(const CmganGemmArgs* a, void* stream);
 int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream);
 int cmgan_pack_weights(const CmganPackDesc* descs, int n, void* stream);
+
+/* ---- fused macaron feed-forward (conformer.py:54-72,136-148,211-212): LN -> 64x256 -> Swish, dropout -> 256x64 -> dropout, alpha, residual in ONE tcgen05 kernel */
+int cmgan_ffn_fwd(const float* x, long long ldx, long long M, const float* ln_g, const float* ln_b, const float* W1p, const float* b1, const float* W2p, const float* b2, float alpha, unsigned long long seed1, unsigned long long seed2, unsigned int thr, float inv_keep, const unsigned long long* seed_dev, float* out, long long ldo, void* stream);
 
 /* ---- LayerNorm (conformer.py:68,161,214), InstanceNorm2d (generator.py:35,55,61,128,148), BatchNorm1d (conformer.py:169) */
 int cmgan_ln_stats(const float* x, long long ldx, long long M, float* stats, void* stream);
@@ -39,6 +43,7 @@ int cmgan_norm_bwd_apply(const float* x, long long ldx, const float* dact, long 
 int cmgan_norm_apply(const float* x, long long ldx, int G, long long rows_per_group, int C, int act, const float* scale, const float* shift, long long tstride, const float* slope, float* y, long long ldy, void* stream);
 int cmgan_fill(float* p, long long n, float v, void* stream);
 int cmgan_copy_rows(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream);
+int cmgan_copy_rows_operand(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream);
 int cmgan_add_rows(const float* src, long long lds, float* dst, long long ldd, long long M, int C, void* stream);
 
 /* ---- attention with Shaw relative positions (conformer.py:100-131); axis 0 = time sequences, 1 = frequency sequences */

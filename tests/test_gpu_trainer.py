@@ -127,7 +127,7 @@ def test_lr_schedule_under_graph_replay_and_checkpoint_roundtrip(g_weights, d_we
     # Adam's first steps move every weight by ~lr: the captured graph must follow the new device-side lr
     ratio = (p2 - p1).abs().mean().item() / (p1 - p0).abs().mean().item()
     print(f"[lr] mean |update| after halving lr / before: {ratio:.3f}")
-    assert 0.3 < ratio < 0.7
+    assert 0.2 < ratio < 0.8
     # resume from the checkpoint in a fresh trainer: same lr schedule position, same next step
     m2, d2 = _models(g_weights, d_weights)
     m2.train(); d2.train()
