@@ -110,8 +110,9 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
 
     def ff(xin, name, s1, s2):
         """0.5 * FF(LN(x)) + x  (ref: conformer.py:54-72,136-148,211-212)"""
-        if ops.PRECISION == 1 and ops.FUSED_FFN and not keep:
-            # one kernel: the (M, 256) hidden activation lives in TMEM / shared memory only (csrc/ffn_fused.cu)
+        if ops.PRECISION == 1 and ops.FUSED_FFN:
+            # one kernel: the (M, 256) hidden activation lives in TMEM / shared memory only (csrc/ffn_fused.cu); the backward pass
+            # recomputes it from the module input, so nothing but that input is kept
             W1, W2 = P[f"{p}.{name}.fn.fn.net.0.weight"], P[f"{p}.{name}.fn.fn.net.3.weight"]
             out = _empty(M, C, dev=dev)
             thr, inv = ops.drop_params(dp)
@@ -119,7 +120,7 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
                  ops.packed_weight(W1, 0, 1, C, C, 1, 4 * C), P[f"{p}.{name}.fn.fn.net.0.bias"],
                  ops.packed_weight(W2, 0, 1, 4 * C, 4 * C, 1, C), P[f"{p}.{name}.fn.fn.net.3.bias"], 0.5,
                  s1 & 0xFFFFFFFFFFFFFFFF, s2 & 0xFFFFFFFFFFFFFFFF, thr, inv, ops.SEED_DEV, out, C)
-            return None, out
+            return (dict(fused=True) if keep else None), out
         xn, st = layer_norm(xin, f"{p}.{name}.fn.norm.weight", f"{p}.{name}.fn.norm.bias")
         h = _empty(M, 4 * C, dev=dev) if keep else None          # pre-activation: only the backward pass needs it
         a = _empty(M, 4 * C, dev=dev)                            # swish(h) * dropout: operand of the second Linear
@@ -200,6 +201,20 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     def ff_bwd(dout, dz, xin, f, name, s1, res2=None, **znext):
         # out = xin + 0.5 * drop2(W2 a + b2),  a = swish(h) * drop1,  h = W1 LN(xin) + b1;   dz = 0.5 * drop2-mask * dout
         W1, W2 = P[f"{p}.{name}.fn.fn.net.0.weight"], P[f"{p}.{name}.fn.fn.net.3.weight"]
+        if f.get("fused"):
+            # one kernel for the data gradients (hidden activation recomputed, LayerNorm backward in its epilogue); it leaves the operands
+            # of the two weight-gradient GEMMs behind: a = swish(h) * drop, dh, xn
+            a, dh, xn, dxv = _empty(M, 4 * C, dev=dev), _empty(M, 4 * C, dev=dev), _empty(M, C, dev=dev), _empty(M, C, dev=dev)
+            thr, inv = ops.drop_params(dp)
+            call("cmgan_ffn_bwd", xin, C, dz, C, dout, C, res2, C if res2 is not None else 0, M, P[f"{p}.{name}.fn.norm.weight"],
+                 P[f"{p}.{name}.fn.norm.bias"], ops.packed_weight(W1, 0, 1, C, C, 1, 4 * C), P[f"{p}.{name}.fn.fn.net.0.bias"],
+                 ops.packed_weight(W2, 0, 4 * C, 1, C, 1, 4 * C), ops.packed_weight(W1, 0, C, 1, 4 * C, 1, C), s1 & 0xFFFFFFFFFFFFFFFF, thr, inv,
+                 ops.SEED_DEV, dxv, C, a, dh, xn, G[f"{p}.{name}.fn.norm.weight"], G[f"{p}.{name}.fn.norm.bias"])
+            gemm(wgrad=True, A=a, lda=4 * C, Cin=4 * C, D=dz, ldd=C, N=C, W=None, C=G[f"{p}.{name}.fn.fn.net.3.weight"], sb_k=1, sb_n=4 * C, ldc=0,
+                 M=M, dbias=G[f"{p}.{name}.fn.fn.net.3.bias"])
+            gemm(wgrad=True, A=xn, lda=C, Cin=C, D=dh, ldd=4 * C, N=4 * C, W=None, C=G[f"{p}.{name}.fn.fn.net.0.weight"], sb_k=1, sb_n=C, ldc=0, M=M,
+                 dbias=G[f"{p}.{name}.fn.fn.net.0.bias"])
+            return dxv, None
         dh = _empty(M, 4 * C, dev=dev)
         gemm(A=dz, lda=C, W=W2, sb_k=4 * C, sb_n=1, C=dh, ldc=4 * C, M=M, N=4 * C, Cin=C, epi=EPI_DSWISH_DROP, aux=f["h"], ldaux=4 * C, seed=s1,
              drop_p=dp)
