@@ -34,7 +34,15 @@ __device__ __forceinline__ float cmgan_rna_tf32(float x) {
 __device__ __forceinline__ float cmgan_maybe_rna(float x, int on) { return on ? cmgan_rna_tf32(x) : x; }
 
 // ---- math ----------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// 1 / (1 + 2^(-x log2 e)) on the raw MUFU approximations (flush-to-zero): 2 MUFU + 2 FP instructions.  __expf / __fdividef wrap the same
+// two instructions in denormal / range handling (3x the instructions) that a sigmoid does not need: exp underflow gives exactly 1,
+// overflow gives 1 / inf = 0.
+__device__ __forceinline__ float sigmoidf_(float x) {
+    float e, s;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
+    return s;
+}
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x * sigmoid(x)]
 __device__ __forceinline__ float dswishf_(float x) {

@@ -583,6 +583,17 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
                         dv[2 * p] = to_tf32(__uint_as_float(rd[2 * p]) * d0 * (s0 * (1.f + h0 * (1.f - s0))));
                         dv[2 * p + 1] = to_tf32(__uint_as_float(rd[2 * p + 1]) * d1 * (s1 * (1.f + h1 * (1.f - s1))));
                     }
+                    // the ring first: mbarrier.arrive releases every earlier write of the thread, global ones included -- stores to HBM issued before it
+                    // would have to drain (MEMBAR) before the tensor pipe may see the chunk
+                    if (hf == 0) mbar_wait(hid_empty(c2), (uint32_t)(((cj >> 1) & 1) ^ 1));        // the third contraction has read the previous occupant
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) st_shared_v4(dst + sw_off(rloc, hf * 4 + c), dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+                    if (hf == 1) {
+                        fence_proxy_async();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(hid_full(c2));
+                    }
                     if (ok) {
                         float4* ao = reinterpret_cast<float4*>(g.a_out + row * HID + n0);
                         float4* go = reinterpret_cast<float4*>(g.dh_out + row * HID + n0);
@@ -592,14 +603,8 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
                             go[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
                         }
                     }
-                    if (hf == 0) mbar_wait(hid_empty(c2), (uint32_t)(((cj >> 1) & 1) ^ 1));        // the third contraction has read the previous occupant
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) st_shared_v4(dst + sw_off(rloc, hf * 4 + c), dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
                 }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(hid_full(c2));
+
             }
         }
     } else {

@@ -52,6 +52,24 @@ def main():
         gemm(A=act, lda=256, W=W2, sb_k=1, sb_n=256, bias=b2, C=outs[i], ldc=64, M=M, N=64, Cin=256, epi=EPI_DROP_RES, alpha=0.5, R=xs[i], ldr=64, seed=12,
              drop_p=a.drop)
 
+    # ---- backward: fused kernel vs the three launches it replaces (data gradients only; the weight-gradient GEMMs are common to both)
+    douts = [torch.randn(M, 64, device=dev) for _ in range(nbuf)]
+    dzs = [torch.randn(M, 64, device=dev) for _ in range(nbuf)]
+    dxs = [torch.empty(M, 64, device=dev) for _ in range(nbuf)]
+    a_o, dh_o, xn_o = torch.empty(M, 256, device=dev), torch.empty(M, 256, device=dev), torch.empty(M, 64, device=dev)
+    dg, db = torch.zeros(64, device=dev), torch.zeros(64, device=dev)
+    W2tp, W1tp = ops.packed_weight(W2, 0, 256, 1, 64, 1, 256), ops.packed_weight(W1, 0, 64, 1, 256, 1, 64)
+
+    def fused_bwd(i):
+        call("cmgan_ffn_bwd", xs[i], 64, dzs[i], 64, douts[i], 64, None, 0, M, g, b, W1p, b1, W2tp, W1tp, 11, thr, inv, None, dxs[i], 64, a_o, dh_o, xn_o, dg, db)
+
+    dln = torch.empty(M, 64, device=dev)
+
+    def unfused_bwd(i):
+        gemm(A=dzs[i], lda=64, W=W2, sb_k=256, sb_n=1, C=dh_o, ldc=256, M=M, N=256, Cin=64, epi=ops.EPI_DSWISH_DROP, aux=h, ldaux=256, seed=11, drop_p=a.drop)
+        gemm(A=dh_o, lda=256, W=W1, sb_k=64, sb_n=1, C=dln, ldc=64, M=M, N=64, Cin=256)
+        call("cmgan_ln_bwd", dln, 64, xs[i], 64, st, g, M, douts[i], 64, None, 0, dxs[i], 64, dg, db)
+
     def timeit(fn):
         for i in range(nbuf):
             fn(i)
@@ -75,12 +93,19 @@ def main():
     for name, fn in (("fused", fused), ("unfused_eval", lambda i: unfused(i, False)), ("unfused_train", lambda i: unfused(i, True))):
         us = timeit(fn)
         res[name] = {"us": us, "tflops": flop / us / 1e6, "compulsory_gbs": byts / us / 1e3}
+    unfused(0, True)
+    bflop = 2.0 * M * 64 * 256 * 3
+    bbytes = 4.0 * M * (64 * 5 + 256 * 2)
+    for name, fn in (("fused_bwd", fused_bwd), ("unfused_bwd", unfused_bwd)):
+        us = timeit(fn)
+        res[name] = {"us": us, "tflops": bflop / us / 1e6, "io_gbs": bbytes / us / 1e3}
     print(json.dumps(res))
     if a.profile:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        for i in range(3):
+        for i in range(2):
             fused(i % nbuf)
+            fused_bwd(i % nbuf)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
 
