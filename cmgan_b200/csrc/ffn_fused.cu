@@ -9,16 +9,18 @@
 //
 //   warps 0-3   LayerNorm producers (thread = row): load x (one tile ahead of the tensor pipe), LayerNorm in registers (no shuffles),
 //               write the normalised tf32 row into the K-major A tile.
-//   warps 14-17 output epilogue (thread = row): acc2 from TMEM, bias, dropout, alpha, residual (x re-read from L2), store.
+//   last 8      output epilogue (thread = half a row): residual prefetched from L2, acc2 from TMEM, bias, dropout, alpha, store.
 //   warp 4      TMEM allocation; one lane issues every tcgen05.mma / tcgen05.commit:
 //                 GEMM1  H[:, 64 q .. 64 q + 63] = xn W1^T in four N = 64 quarters (the activation warps start on quarter 0 while
 //                        quarters 1-3 are still in the tensor pipe; quarter q of the NEXT tile is issued as soon as the activation
 //                        warps have drained quarter q of this one),
 //                 GEMM2  acc2 += a_chunk W2_chunk^T over eight K = 32 chunks as they arrive in the ring (double-buffered accumulator).
 //   warp 5      weight images -> shared memory by cp.async.bulk, once.
-//   warps 6-13  activation: tcgen05.ld 32 columns of H -> + b1 -> swish -> counter-based dropout -> round to tf32 -> st.shared into
+//   warps 6-13  activation (2 groups x 4 lane quarters, chunks round-robin): tcgen05.ld 32 columns of H -> + b1 -> swish -> counter-based dropout -> round to tf32 -> st.shared into
 //               the ring slot in the UMMA K-major swizzled layout -> fence.proxy.async -> mbarrier.
 // All mbarrier waits are bounded (tc_ptx.cuh): a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched from the driver at run time)
+
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 #include "tc_ptx.cuh"
@@ -32,7 +34,9 @@ constexpr int W1_BYTES = 2 * HID * 128;               // 2 K-chunks x 256 rows x
 constexpr int W2_BYTES = 8 * C * 128;                 // 8 K-chunks x  64 rows x 128 B = 64 KB
 constexpr int XN_BYTES = 2 * CHUNK_BYTES;             // A tile of GEMM1: 128 x 64
 constexpr int RING = 3;                               // hidden chunks in flight between the activation warps and GEMM2
-constexpr int NTHREADS = 576;                         // 18 warps: 4 LayerNorm + MMA + weights + 8 activation + 4 output
+constexpr int NACT_GROUPS = 2;                        // activation groups of 4 warps (one per TMEM lane quarter), chunks round-robin
+constexpr int NEPI = 8;                               // output warps: two per TMEM lane quarter, 32 of the 64 columns each
+constexpr int NTHREADS = 32 * (6 + 4 * NACT_GROUPS + NEPI);      // 4 LayerNorm + MMA + weights + activation + output warps
 constexpr int TMEM_COLS = 512;                        // H: 4 x 64, acc2: 2 x 64
 constexpr int SMEM_FWD = 1024 + W1_BYTES + W2_BYTES + XN_BYTES + RING * CHUNK_BYTES + 2048;
 
@@ -46,6 +50,7 @@ struct FfnFwdArgs {
     float alpha;
     unsigned long long seed1, seed2; unsigned int thr; float inv_keep;
     const unsigned long long* seed_dev;
+    long long* dbg;                  // optional timeline (CTA 0): clock64 stamps, 64 per warp (tools/bench_ffn.py --timeline)
 };
 
 // byte offset of (row r, 16-byte unit c of the row's 128 bytes) inside a K-major SWIZZLE_128B chunk
@@ -54,6 +59,11 @@ __device__ __forceinline__ uint32_t sw_off(int r, int c) { return (uint32_t)(r *
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+
+#define FFN_STAMP(slot)                                                                                   \
+    do {                                                                                                  \
+        if (g.dbg && blockIdx.x == 0 && lane == 0 && (slot) < 64) g.dbg[warp * 64 + (slot)] = clock64();  \
+    } while (0)
 
 __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_constant__ FfnFwdArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
         mbar_init(xn_full, 4); mbar_init(xn_empty, 1); mbar_init(wready, 1);
         for (int q = 0; q < 4; ++q) mbar_init(hq_full(q), 1);
         for (int s = 0; s < RING; ++s) { mbar_init(hid_full(s), 4); mbar_init(hid_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), NEPI); }
         fence_barrier_init();
     }
     for (int i = tid; i < 448; i += NTHREADS)
@@ -113,7 +123,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < 64; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
             const float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
+            FFN_STAMP(3 * lt);
             mbar_wait(xn_empty, (uint32_t)((lt & 1) ^ 1));          // GEMM1 of the previous tile has read the A tile
+            FFN_STAMP(3 * lt + 1);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 float o[4];
@@ -124,10 +136,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(xn_full);
+            FFN_STAMP(3 * lt + 2);
         }
-    } else if (warp >= 14) {
-        // ================================ output epilogue (warps 14-17) ================================
+    } else if (warp >= 6 + 4 * NACT_GROUPS) {
+        // ================================ output epilogue (last NEPI warps) ================================
+        // thread = half a row (32 columns).  The residual half row is requested BEFORE the wait for the accumulator, so its L2 latency
+        // (the row was read by this CTA one tile ago) hides behind the tile's second contraction instead of serialising behind it.
+        const int ew = warp - (6 + 4 * NACT_GROUPS);
         const int lq = warp & 3;                    // TMEM lane quarter
+        const int hv = ew >> 2;                     // column half
         const int rloc = lq * 32 + lane;
         const uint32_t seed2_32 = cmgan_seed32(cmgan_eff_seed(g.seed2, g.seed_dev));
         const uint32_t thr16 = g.thr >> 16;
@@ -135,22 +152,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int buf = lt & 1;
             const long row = ((long)blockIdx.x + (long)lt * gridDim.x) * BM + rloc;
+            const bool ok = row < g.M;
+            float4 xv[8];
+            if (ok) {
+                const float4* xr = reinterpret_cast<const float4*>(g.x + row * g.ldx) + hv * 8;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) xv[c4] = __ldg(xr + c4);
+            }
+            FFN_STAMP(3 * lt);
             mbar_wait(acc_full(buf), (uint32_t)((lt >> 1) & 1));
+            FFN_STAMP(3 * lt + 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)(HID + buf * C) + ((uint32_t)(lq * 32) << 16);
-            uint32_t r[64];
-            tmem_ld16_nowait(taddr, r); tmem_ld16_nowait(taddr + 16, r + 16); tmem_ld16_nowait(taddr + 32, r + 32); tmem_ld16_nowait(taddr + 48, r + 48);
+            const uint32_t taddr = tmem_base + (uint32_t)(HID + buf * C + hv * 32) + ((uint32_t)(lq * 32) << 16);
+            float r[32];
+            tmem_ld16f_nowait(taddr, r); tmem_ld16f_nowait(taddr + 16, r + 16);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(buf));
-            if (row < g.M) {
-                float* orow = g.out + row * g.ldo;
-                const float4* xr = reinterpret_cast<const float4*>(g.x + row * g.ldx);      // residual: read by this CTA a tile ago (L2)
-                const uint32_t pair0 = (uint32_t)(((unsigned long long)row * C) >> 1);
+            if (ok) {
+                float4* orow = reinterpret_cast<float4*>(g.out + row * g.ldo) + hv * 8;
+                const uint32_t pair0 = (uint32_t)(((unsigned long long)row * C + (unsigned long long)(hv * 32)) >> 1);
 #pragma unroll
-                for (int c4 = 0; c4 < 16; ++c4) {
-                    const float4 xv = __ldg(xr + c4);
+                for (int c4 = 0; c4 < 8; ++c4) {
                     float ds[4] = {1.f, 1.f, 1.f, 1.f};
                     if (drop_on) {
                         const uint32_t pr = pair0 + 2u * c4;
@@ -158,14 +182,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
                         ds[0] = (h0 & 0xFFFFu) >= thr16 ? g.inv_keep : 0.f; ds[1] = (h0 >> 16) >= thr16 ? g.inv_keep : 0.f;
                         ds[2] = (h1 & 0xFFFFu) >= thr16 ? g.inv_keep : 0.f; ds[3] = (h1 >> 16) >= thr16 ? g.inv_keep : 0.f;
                     }
+                    const int k = hv * 32 + 4 * c4;
                     float4 o;
-                    o.x = fmaf(g.alpha * ds[0], __uint_as_float(r[4 * c4 + 0]) + b2s[4 * c4 + 0], xv.x);
-                    o.y = fmaf(g.alpha * ds[1], __uint_as_float(r[4 * c4 + 1]) + b2s[4 * c4 + 1], xv.y);
-                    o.z = fmaf(g.alpha * ds[2], __uint_as_float(r[4 * c4 + 2]) + b2s[4 * c4 + 2], xv.z);
-                    o.w = fmaf(g.alpha * ds[3], __uint_as_float(r[4 * c4 + 3]) + b2s[4 * c4 + 3], xv.w);
-                    reinterpret_cast<float4*>(orow)[c4] = o;
+                    o.x = fmaf(g.alpha * ds[0], r[4 * c4 + 0] + b2s[k + 0], xv[c4].x);
+                    o.y = fmaf(g.alpha * ds[1], r[4 * c4 + 1] + b2s[k + 1], xv[c4].y);
+                    o.z = fmaf(g.alpha * ds[2], r[4 * c4 + 2] + b2s[k + 2], xv[c4].z);
+                    o.w = fmaf(g.alpha * ds[3], r[4 * c4 + 3] + b2s[k + 3], xv[c4].w);
+                    orow[c4] = o;
                 }
             }
+            FFN_STAMP(3 * lt + 2);
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
@@ -202,6 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
                     const long gch = (long)lt * 8 + j;
                     const int s = (int)(gch % RING);
                     mbar_wait(hid_full(s), (uint32_t)((gch / RING) & 1));
+                    FFN_STAMP((int)gch);
                     tc_fence_after();
                     const uint64_t adesc = make_desc_sw128(sRing + s * CHUNK_BYTES, 16, 1024);
                     const uint64_t bdesc = make_desc_sw128(sW2 + j * (C * 128), 16, 1024);
@@ -229,51 +256,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
         }
         __syncwarp();
     } else if (warp >= 6) {
-        // ================================ activation warps (6-13) ================================
+        // ================================ activation warps ================================
+        // group g (4 warps, one per TMEM lane quarter) takes hidden chunks g, g + NACT_GROUPS, ... of the CTA's chunk stream (8 per tile)
         const int lq = warp & 3;                    // TMEM lane quarter this warp may touch
-        const int half = (warp - 6) >> 2;           // quarters {half, half + 2} of H
+        const int grp = (warp - 6) >> 2;
         const int rloc = lq * 32 + lane;            // row within the tile
         const uint32_t seed1_32 = cmgan_seed32(cmgan_eff_seed(g.seed1, g.seed_dev));
         const uint32_t thr16 = g.thr >> 16;
         const bool drop_on = g.thr != 0u;
-        for (int lt = 0; lt < my_tiles; ++lt) {
+        const long nchunks = 8L * my_tiles;
+        for (long gch = grp; gch < nchunks; gch += NACT_GROUPS) {
+            const int sl = (int)(gch % RING);
+            const uint32_t dst = sRing + sl * CHUNK_BYTES;
+            const int lt = (int)(gch >> 3), j = (int)(gch & 7), q = j >> 1;
             const long row = ((long)blockIdx.x + (long)lt * gridDim.x) * BM + rloc;
-            for (int qq = 0; qq < 2; ++qq) {
-                const int q = half + 2 * qq;
-                mbar_wait(hq_full(q), (uint32_t)(lt & 1));
-                tc_fence_after();
+            const int n0 = j * 32;
+            const int ck = (int)(gch / NACT_GROUPS);
+            FFN_STAMP(4 * ck);
+            mbar_wait(hq_full(q), (uint32_t)(lt & 1));
+            FFN_STAMP(4 * ck + 1);
+            tc_fence_after();
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + (uint32_t)n0 + ((uint32_t)(lq * 32) << 16);
+            tmem_ld16_nowait(taddr, r); tmem_ld16_nowait(taddr + 16, r + 16);
+            tmem_wait_ld();
+            float a[32];
+            const uint32_t pair0 = (uint32_t)(((unsigned long long)row * HID + (unsigned long long)n0) >> 1);
 #pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const int j = 2 * q + c2, n0 = q * 64 + c2 * 32;
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + (uint32_t)n0 + ((uint32_t)(lq * 32) << 16);
-                    tmem_ld16_nowait(taddr, r); tmem_ld16_nowait(taddr + 16, r + 16);
-                    tmem_wait_ld();
-                    float a[32];
-                    const uint32_t pair0 = (uint32_t)(((unsigned long long)row * HID + (unsigned long long)n0) >> 1);
-#pragma unroll
-                    for (int p = 0; p < 16; ++p) {
-                        float d0 = 1.f, d1 = 1.f;
-                        if (drop_on) {
-                            const uint32_t h = cmgan_mix32(((pair0 + (uint32_t)p) * 0x9E3779B1u) ^ seed1_32);
-                            d0 = (h & 0xFFFFu) >= thr16 ? g.inv_keep : 0.f; d1 = (h >> 16) >= thr16 ? g.inv_keep : 0.f;
-                        }
-                        const float v0 = __uint_as_float(r[2 * p]) + b1s[n0 + 2 * p], v1 = __uint_as_float(r[2 * p + 1]) + b1s[n0 + 2 * p + 1];
-                        a[2 * p] = to_tf32(swishf_(v0) * d0);
-                        a[2 * p + 1] = to_tf32(swishf_(v1) * d1);
-                    }
-                    const long gch = (long)lt * 8 + j;
-                    const int s = (int)(gch % RING);
-                    mbar_wait(hid_empty(s), (uint32_t)(((gch / RING) & 1) ^ 1));
-                    const uint32_t dst = sRing + s * CHUNK_BYTES;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) st_shared_v4(dst + sw_off(rloc, c), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
-                    fence_proxy_async();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(hid_full(s));
+            for (int p = 0; p < 16; ++p) {
+                float d0 = 1.f, d1 = 1.f;
+                if (drop_on) {
+                    const uint32_t h = cmgan_mix32(((pair0 + (uint32_t)p) * 0x9E3779B1u) ^ seed1_32);
+                    d0 = (h & 0xFFFFu) >= thr16 ? g.inv_keep : 0.f; d1 = (h >> 16) >= thr16 ? g.inv_keep : 0.f;
                 }
+                const float v0 = __uint_as_float(r[2 * p]) + b1s[n0 + 2 * p], v1 = __uint_as_float(r[2 * p + 1]) + b1s[n0 + 2 * p + 1];
+                a[2 * p] = to_tf32(swishf_(v0) * d0);
+                a[2 * p + 1] = to_tf32(swishf_(v1) * d1);
             }
+            FFN_STAMP(4 * ck + 2);
+            mbar_wait(hid_empty(sl), (uint32_t)(((gch / RING) & 1) ^ 1));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) st_shared_v4(dst + sw_off(rloc, c), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hid_full(sl));
+            FFN_STAMP(4 * ck + 3);
         }
     }
     __syncthreads();
@@ -292,20 +320,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffn_fwd_kernel(const __grid_const
 //
 // with dz = alpha * m2 * dout materialised by the producer of dout.  Outputs for the weight gradients: a, dh (M, 256), xn (M, 64), all
 // rounded to tf32.  Per 128-row tile: H and DA are born in TMEM quarter by quarter (64 hidden columns), the activation warps turn them
-// into a / dh, dh goes through a two-slot K-major ring into the third contraction (accumulator double-buffered in TMEM), and the
-// epilogue warps run the LayerNorm backward of their rows straight from TMEM.
-// Shared memory (fp32 operands are fat): W1 (64 KB, for H) and W1 in its K = hidden form (64 KB, for dxn) are resident, W2 (for DA)
-// streams through three 8 KB slots (L2-resident), and xn / dz take turns in ONE 32 KB A tile.
-// Roles are warpgroup-aligned so that setmaxnreg can move registers from the issue / copy warps to the epilogue warps:
-//   WG0 warps 0-3   row producers: x -> LayerNorm -> A tile (+ xn to HBM, row statistics to smem), then dz -> A tile
-//   WG1 warp 4      MMA issuer (event loop over: H quarter, DA quarter, dh chunk; probes instead of blocking waits)
-//       warp 5      weight copies (resident images once, W2 pieces continuously)
-//   WG2-3 warps 8-15  activation (two groups alternating over the quarters)
-//   WG4 warps 16-19 LayerNorm-backward epilogue
-constexpr int NT_BWD = 640;
-constexpr int W2_PIECE = 64 * 128;                  // one (quarter, K chunk) piece of the DA weight: 64 rows x 128 B
+// into a / dh chunks in two K-major shared-memory rings; the dh ring feeds the third contraction (accumulator double-buffered in TMEM)
+// and BOTH rings are written to HBM by TMA (cp.async.bulk.tensor stores un-swizzle them into row-major (M, 256)): the activation warps
+// never touch global memory.  The epilogue warps (thread = half a row, inputs prefetched before the accumulator is ready) run the
+// LayerNorm backward straight from TMEM.
+// Shared memory (fp32 operands are fat): no weight is resident -- W1 (for H), W2 (for DA) and W1 in its K = hidden form (for dxn) stream
+// through three 8 KB slots each (192 KB per tile out of L2), which leaves room for separate xn and dz A tiles (the next tile's H / DA
+// quarters are issued while this tile's are still being consumed) and for the two output rings.
+//   warps 0-3    row producers: x -> LayerNorm -> A tile (+ xn to HBM, row statistics to smem), then dz -> A tile
+//   warp 4       MMA issuer (event loop over: H quarter, DA quarter, dh chunk; probes instead of blocking waits)
+//   warp 5       weight copies (three lanes, one per stream: W1 / W2 / W1t pieces continuously, 48 KB per quarter)
+//   warp 6       TMA stores of the a / dh chunks
+//   warps 8-15   activation (two groups, chunks round-robin; one warp per TMEM lane quarter in each)
+//   warps 16-23  LayerNorm-backward epilogue (two warps per lane quarter, 32 of the 64 channels each)
+constexpr int NT_BWD = 768;
+constexpr int W_PIECE = 64 * 128;                   // one 64-row x 32-float piece of a streamed weight image (8 KB)
 constexpr int NPIECE = 3;
-constexpr int SMEM_BWD = 1024 + W1_BYTES + W2_BYTES /* W1 in K = hidden form */ + XN_BYTES + 2 * CHUNK_BYTES + NPIECE * W2_PIECE + 2 * BM * 8 + 1536 + 256;
+constexpr int SMEM_BWD = 1024 + 2 * XN_BYTES + 4 * CHUNK_BYTES + 3 * NPIECE * W_PIECE + 2 * BM * 8 + 2 * 2 * BM * 8 + 1536 + 512;
 
 struct FfnBwdArgs {
     const float* x; long long ldx;
@@ -313,13 +344,14 @@ struct FfnBwdArgs {
     const float* dout; long long lddo;
     const float* res2; long long ldr2;
     float* dx; long long lddx;
-    float* a_out; float* dh_out; float* xn_out;
+    float* xn_out;
     const float* ln_g; const float* ln_b; const float* b1;
     const float* W1p; const float* W2tp; const float* W1tp;
     float* dgamma; float* dbeta;
     long long M;
     unsigned long long seed1; unsigned int thr; float inv_keep;
     const unsigned long long* seed_dev;
+    long long* dbg;
 };
 
 template <int N>
@@ -327,59 +359,44 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// column sums over the 32 lanes of a warp of a 32-entry per-lane array: afterwards v[0] holds the total of entry `lane`
-__device__ __forceinline__ void warp_transpose_sum32(float v[32], int lane) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 2;
-        const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    {
-        const bool up = lane & 1;
-        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
+// TMA store of one K-major SWIZZLE_128B chunk (128 rows x 32 floats) to a row-major (M, 256) tensor; rows past M are clipped by the unit
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constant__ FfnBwdArgs g) {
+__global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constant__ FfnBwdArgs g, const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmDh) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sW1 = base, sW1t = sW1 + W1_BYTES, sA = sW1t + W2_BYTES, sRing = sA + XN_BYTES, sW2 = sRing + 2 * CHUNK_BYTES;
-    const uint32_t sStat = sW2 + NPIECE * W2_PIECE;                 // float2 [2][128]: (mean, rstd) of the rows of the tile
-    const uint32_t sPar = sStat + 2 * BM * 8;                       // gamma[64] beta[64] b1[256]
+    const uint32_t sXn = base, sDz = sXn + XN_BYTES, sRingD = sDz + XN_BYTES, sRingA = sRingD + 2 * CHUNK_BYTES, sW2 = sRingA + 2 * CHUNK_BYTES;
+    const uint32_t sW1t = sW2 + NPIECE * W_PIECE, sW1 = sW1t + NPIECE * W_PIECE;
+    const uint32_t sStat = sW1 + NPIECE * W_PIECE;                 // float2 [2][128]: (mean, rstd) of the rows of the tile
+    const uint32_t sExch = sStat + 2 * BM * 8;                      // float2 [2 tiles][2 halves][128]: partial (sum g, sum g xhat) of a half row
+    const uint32_t sPar = sExch + 2 * 2 * BM * 8;                   // gamma[64] beta[64] b1[256]
     float2* stat = reinterpret_cast<float2*>(base_ptr + (sStat - base));
+    float2* exch = reinterpret_cast<float2*>(base_ptr + (sExch - base));
     float* par = reinterpret_cast<float*>(base_ptr + (sPar - base));
     const uint32_t bars = sPar + 1536;
-    const uint32_t xn_full = bars, dz_full = bars + 8, a_free = bars + 16, wready = bars + 24;
+    const uint32_t xn_full = bars, dz_full = bars + 8, xn_free = bars + 16, dz_free = bars + 24;
     auto h_full = [&](int q) { return bars + 32u + 8u * q; };        // [4]
     auto da_full = [&](int s) { return bars + 64u + 8u * s; };       // [2]
     auto hid_full = [&](int s) { return bars + 80u + 8u * s; };      // [2]
-    auto hid_empty = [&](int s) { return bars + 96u + 8u * s; };     // [2]
+    auto hid_empty = [&](int s) { return bars + 96u + 8u * s; };     // [2]   two arrivals: tensor pipe done (commit) + TMA stores have read the slot
     auto acc_full = [&](int b) { return bars + 112u + 8u * b; };     // [2]
     auto acc_empty = [&](int b) { return bars + 128u + 8u * b; };    // [2]
     auto w2_full = [&](int s) { return bars + 144u + 8u * s; };      // [3]
     auto w2_empty = [&](int s) { return bars + 168u + 8u * s; };     // [3]
-    const uint32_t tmem_ptr_addr = bars + 192u;
+    auto w1t_full = [&](int s) { return bars + 192u + 8u * s; };     // [3]
+    auto w1t_empty = [&](int s) { return bars + 216u + 8u * s; };    // [3]
+    auto w1_full = [&](int s) { return bars + 240u + 8u * s; };      // [3]
+    auto w1_empty = [&](int s) { return bars + 264u + 8u * s; };     // [3]
+    const uint32_t tmem_ptr_addr = bars + 288u;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (int)((g.M + BM - 1) / BM);
@@ -387,10 +404,10 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
     const int NQ = 4 * my_tiles;
 
     if (tid == 0) {
-        mbar_init(xn_full, 4); mbar_init(dz_full, 4); mbar_init(a_free, 1); mbar_init(wready, 1);
+        mbar_init(xn_full, 4); mbar_init(dz_full, 4); mbar_init(xn_free, 1); mbar_init(dz_free, 1);
         for (int q = 0; q < 4; ++q) mbar_init(h_full(q), 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(da_full(s), 1); mbar_init(hid_full(s), 4); mbar_init(hid_empty(s), 1); mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
-        for (int s = 0; s < NPIECE; ++s) { mbar_init(w2_full(s), 1); mbar_init(w2_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(da_full(s), 1); mbar_init(hid_full(s), 4); mbar_init(hid_empty(s), 2); mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
+        for (int s = 0; s < NPIECE; ++s) { mbar_init(w2_full(s), 1); mbar_init(w2_empty(s), 1); mbar_init(w1t_full(s), 1); mbar_init(w1t_empty(s), 1); mbar_init(w1_full(s), 1); mbar_init(w1_empty(s), 1); }
         fence_barrier_init();
     }
     for (int i = tid; i < 384; i += NT_BWD) par[i] = i < 64 ? __ldg(g.ln_g + i) : i < 128 ? __ldg(g.ln_b + i - 64) : __ldg(g.b1 + i - 128);
@@ -404,8 +421,11 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
     // TMEM columns: H quarters [0, 256), DA slots [256, 384), dxn accumulators [384, 512)
     constexpr uint32_t T_DA = 256, T_ACC = 384;
 
+    // register budget: 768 threads start with 80 each; the issue / copy warpgroup hands 24 x 128 back and the producers (64 row values in
+    // flight) take them.  Local-memory spills go to L2 here (the L1 carve-out is all shared memory), so every role is written to fit.
     if (warp < 4) {
-        // ================================ WG0: row producers ================================
+        // ================================ row producers ================================
+        reg_inc<104>();
         for (int lt = 0; lt < my_tiles; ++lt) {
             const long row = ((long)blockIdx.x + (long)lt * gridDim.x) * BM + tid;
             const bool ok = row < g.M;
@@ -435,9 +455,11 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
             }
             if (lt >= 2) mbar_wait(acc_empty(lt & 1), (uint32_t)(((lt - 2) >> 1) & 1));     // the epilogue of tile lt - 2 has read its row statistics
             stat[(lt & 1) * BM + tid] = make_float2(mean, rstd);
-            if (lt > 0) mbar_wait(a_free, 1u);                       // dz of the previous tile has been consumed (phase 2 lt - 1)
+            FFN_STAMP(4 * lt);
+            if (lt > 0) mbar_wait(xn_free, (uint32_t)((lt - 1) & 1));     // every H quarter of the previous tile has been issued
+            FFN_STAMP(4 * lt + 1);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) st_shared_v4(sA + (uint32_t)(c >> 3) * CHUNK_BYTES + sw_off(tid, c & 7), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            for (int c = 0; c < 16; ++c) st_shared_v4(sXn + (uint32_t)(c >> 3) * CHUNK_BYTES + sw_off(tid, c & 7), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(xn_full);
@@ -449,18 +471,20 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 64; ++k) v[k] = 0.f;
             }
-            mbar_wait(a_free, 0u);                                   // H of this tile has read xn (phase 2 lt)
+            FFN_STAMP(4 * lt + 2);
+            if (lt > 0) mbar_wait(dz_free, (uint32_t)((lt - 1) & 1));     // every DA quarter of the previous tile has been issued
+            FFN_STAMP(4 * lt + 3);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) st_shared_v4(sA + (uint32_t)(c >> 3) * CHUNK_BYTES + sw_off(tid, c & 7), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            for (int c = 0; c < 16; ++c) st_shared_v4(sDz + (uint32_t)(c >> 3) * CHUNK_BYTES + sw_off(tid, c & 7), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(dz_full);
         }
     } else if (warp < 8) {
-        // ================================ WG1: MMA issuer (warp 4), weight copies (warp 5) ================================
+        // ================================ MMA issuer + TMA stores (warp 4), weight copies (warp 5) ================================
+        reg_dec<56>();
         if (warp == 4 && lane == 0 && my_tiles > 0) {
             const uint32_t idesc64 = make_idesc_tf32(BM, 64, 0, 0);
-            mbar_wait(wready, 0);
             int Gh = 0, Gd = 0;              // next H / DA quarter to issue (global quarter index = 4 tile + quarter)
             long cj = 0;                     // next dh chunk to consume (8 per tile)
             const long NC = 8L * my_tiles;
@@ -473,17 +497,22 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
                 if (Gh < NQ && (Gh < 4 || cq > Gh - 4)) {
                     const int t = Gh >> 2, q = Gh & 3;
                     if (xn_tile < t && mbar_test(xn_full, (uint32_t)(t & 1))) { xn_tile = t; tc_fence_after(); }
-                    if (xn_tile >= t) {
+                    const long p0 = 2L * Gh, p1 = p0 + 1;
+                    if (xn_tile >= t && mbar_test(w1_full((int)(p0 % NPIECE)), (uint32_t)((p0 / NPIECE) & 1)) &&
+                        mbar_test(w1_full((int)(p1 % NPIECE)), (uint32_t)((p1 / NPIECE) & 1))) {
+                        tc_fence_after();
 #pragma unroll
                         for (int kc = 0; kc < 2; ++kc) {
-                            const uint64_t adesc = make_desc_sw128(sA + kc * CHUNK_BYTES, 16, 1024);
-                            const uint64_t bdesc = make_desc_sw128(sW1 + kc * (HID * 128) + q * (64 * 128), 16, 1024);
+                            const long p = p0 + kc;
+                            const uint64_t adesc = make_desc_sw128(sXn + kc * CHUNK_BYTES, 16, 1024);
+                            const uint64_t bdesc = make_desc_sw128(sW1 + (uint32_t)(p % NPIECE) * W_PIECE, 16, 1024);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma_tf32(tmem_base + (uint32_t)(q * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc64, (kc | k) != 0 ? 1u : 0u);
+                            umma_commit(w1_empty((int)(p % NPIECE)));
                         }
                         umma_commit(h_full(q));
-                        if (q == 3) umma_commit(a_free);             // phase 2 t: xn consumed, dz may take the A tile
+                        if (q == 3) umma_commit(xn_free);            // xn of tile t consumed: the producers may write the next tile's
                         ++Gh; progress = true;
                     }
                 }
@@ -498,31 +527,33 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
 #pragma unroll
                         for (int kc = 0; kc < 2; ++kc) {
                             const long p = p0 + kc;
-                            const uint64_t adesc = make_desc_sw128(sA + kc * CHUNK_BYTES, 16, 1024);
-                            const uint64_t bdesc = make_desc_sw128(sW2 + (uint32_t)(p % NPIECE) * W2_PIECE, 16, 1024);
+                            const uint64_t adesc = make_desc_sw128(sDz + kc * CHUNK_BYTES, 16, 1024);
+                            const uint64_t bdesc = make_desc_sw128(sW2 + (uint32_t)(p % NPIECE) * W_PIECE, 16, 1024);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma_tf32(tmem_base + T_DA + (uint32_t)((Gd & 1) * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc64, (kc | k) != 0 ? 1u : 0u);
                             umma_commit(w2_empty((int)(p % NPIECE)));
                         }
                         umma_commit(da_full(Gd & 1));
-                        if (q == 3) umma_commit(a_free);             // phase 2 t + 1: dz consumed, xn of the next tile may take the A tile
+                        if (q == 3) umma_commit(dz_free);
                         ++Gd; progress = true;
                     }
                 }
-                // ---- dh chunk -> dxn accumulator
+                // ---- a / dh chunk: dh -> dxn accumulator; both chunks -> HBM by TMA
                 {
                     const int lt = (int)(cj >> 3), j = (int)(cj & 7), buf = lt & 1, sl = (int)(cj & 1);
-                    bool ready = mbar_test(hid_full(sl), (uint32_t)((cj >> 1) & 1));
+                    bool ready = mbar_test(hid_full(sl), (uint32_t)((cj >> 1) & 1)) && mbar_test(w1t_full((int)(cj % NPIECE)), (uint32_t)((cj / NPIECE) & 1));
                     if (ready && j == 0) ready = mbar_test(acc_empty(buf), (uint32_t)(((lt >> 1) & 1) ^ 1));
                     if (ready) {
+                        FFN_STAMP((int)cj);
                         tc_fence_after();
-                        const uint64_t adesc = make_desc_sw128(sRing + sl * CHUNK_BYTES, 16, 1024);
-                        const uint64_t bdesc = make_desc_sw128(sW1t + j * (C * 128), 16, 1024);
+                        const uint64_t adesc = make_desc_sw128(sRingD + sl * CHUNK_BYTES, 16, 1024);
+                        const uint64_t bdesc = make_desc_sw128(sW1t + (uint32_t)(cj % NPIECE) * W_PIECE, 16, 1024);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_tf32(tmem_base + T_ACC + (uint32_t)(buf * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc64, (j | k) != 0 ? 1u : 0u);
-                        umma_commit(hid_empty(sl));
+                        umma_commit(hid_empty(sl));                  // 1st of the slot's two releases
+                        umma_commit(w1t_empty((int)(cj % NPIECE)));
                         if (j == 7) umma_commit(acc_full(buf));
                         ++cj; progress = true;
                     }
@@ -530,143 +561,194 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
                 if (progress) idle = 0;
                 else if (++idle > (1u << 27)) __trap();           // protocol bug: fail loudly instead of hanging the device
             }
-        } else if (warp == 5 && lane == 0 && my_tiles > 0) {
-            mbar_arrive_expect_tx(wready, (uint32_t)(W1_BYTES + W2_BYTES));
-            for (int i = 0; i < 4; ++i) bulk_g2s(sW1 + i * (W1_BYTES / 4), g.W1p + (long)i * (W1_BYTES / 16), (uint32_t)(W1_BYTES / 4), wready);
-            for (int i = 0; i < 4; ++i) bulk_g2s(sW1t + i * (W2_BYTES / 4), g.W1tp + (long)i * (W2_BYTES / 16), (uint32_t)(W2_BYTES / 4), wready);
+        } else if (warp == 5 && lane < 3 && my_tiles > 0) {
+            // three independent streams of 8 KB pieces, one lane each (a blocked stream must not hold the other two back):
+            // lane 0: H weight (piece p = 2 G + kc), lane 1: DA weight (same indexing), lane 2: dxn weight (piece = chunk index, K chunk 2 q + c2)
             const long NP = 2L * NQ;
-            for (long p = 0; p < NP; ++p) {                         // piece p = (quarter G = p / 2, K chunk p % 2) of the DA weight image
+            for (long p = 0; p < NP; ++p) {
                 const int sl = (int)(p % NPIECE), q = (int)((p >> 1) & 3), kc = (int)(p & 1);
-                mbar_wait(w2_empty(sl), (uint32_t)(((p / NPIECE) & 1) ^ 1));
-                mbar_arrive_expect_tx(w2_full(sl), (uint32_t)W2_PIECE);
-                bulk_g2s(sW2 + sl * W2_PIECE, g.W2tp + ((long)kc * (HID * 128) + (long)q * W2_PIECE) / 4, (uint32_t)W2_PIECE, w2_full(sl));
+                const uint32_t par = (uint32_t)(((p / NPIECE) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_wait(w1_empty(sl), par);
+                    mbar_arrive_expect_tx(w1_full(sl), (uint32_t)W_PIECE);
+                    bulk_g2s(sW1 + sl * W_PIECE, g.W1p + ((long)kc * (HID * 128) + (long)q * W_PIECE) / 4, (uint32_t)W_PIECE, w1_full(sl));
+                } else if (lane == 1) {
+                    mbar_wait(w2_empty(sl), par);
+                    mbar_arrive_expect_tx(w2_full(sl), (uint32_t)W_PIECE);
+                    bulk_g2s(sW2 + sl * W_PIECE, g.W2tp + ((long)kc * (HID * 128) + (long)q * W_PIECE) / 4, (uint32_t)W_PIECE, w2_full(sl));
+                } else {
+                    mbar_wait(w1t_empty(sl), par);
+                    mbar_arrive_expect_tx(w1t_full(sl), (uint32_t)W_PIECE);
+                    bulk_g2s(sW1t + sl * W_PIECE, g.W1tp + ((long)(2 * q + kc) * W_PIECE) / 4, (uint32_t)W_PIECE, w1t_full(sl));
+                }
             }
+        } else if (warp == 6 && lane == 0 && my_tiles > 0) {
+            // a / dh chunks -> HBM by TMA, in ring order; the slot's 2nd release once the unit has read it (the issuer never waits on this)
+            const long NC = 8L * my_tiles;
+            for (long cj = 0; cj < NC; ++cj) {
+                const int lt = (int)(cj >> 3), j = (int)(cj & 7), sl = (int)(cj & 1);
+                mbar_wait(hid_full(sl), (uint32_t)((cj >> 1) & 1));
+                const int row0 = (int)(((long)blockIdx.x + (long)lt * gridDim.x) * BM);
+                tma_store_2d(&tmDh, sRingD + sl * CHUNK_BYTES, j * 32, row0);
+                tma_store_2d(&tmA, sRingA + sl * CHUNK_BYTES, j * 32, row0);
+                bulk_commit();
+                bulk_wait_read<0>();
+                mbar_arrive(hid_empty(sl));
+            }
+            bulk_wait_all<0>();                                      // every a / dh store has landed before the CTA retires
         }
         __syncwarp();
     } else if (warp < 16) {
-        // ================================ WG2-3: activation ================================
+        // ================================ activation (warps 8-15) ================================
+        // group (warp - 8) / 4 takes the chunks of its parity: both groups work on the two halves of the same quarter
         const int lq = warp & 3, grp = (warp - 8) >> 2, rloc = lq * 32 + lane;
         const uint32_t seed1_32 = cmgan_seed32(cmgan_eff_seed(g.seed1, g.seed_dev));
         const uint32_t thr16 = g.thr >> 16;
         const bool drop_on = g.thr != 0u;
-        for (int G = grp; G < NQ; G += 2) {
-            const int lt = G >> 2, q = G & 3;
+        const long NC = 8L * my_tiles;
+        const uint32_t dstD = sRingD + grp * CHUNK_BYTES, dstA = sRingA + grp * CHUNK_BYTES;
+        for (long cj = grp; cj < NC; cj += 2) {
+            const int lt = (int)(cj >> 3), j = (int)(cj & 7), q = j >> 1;
+            const long G = cj >> 1;
             const long row = ((long)blockIdx.x + (long)lt * gridDim.x) * BM + rloc;
-            const bool ok = row < g.M;
+            FFN_STAMP(3 * (int)(cj >> 1));
             mbar_wait(h_full(q), (uint32_t)(lt & 1));
-            mbar_wait(da_full(grp), (uint32_t)((G >> 1) & 1));
+            mbar_wait(da_full((int)(G & 1)), (uint32_t)((G >> 1) & 1));
             tc_fence_after();
+            FFN_STAMP(3 * (int)(cj >> 1) + 1);
 #pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-                const long cj = 8L * lt + 2 * q + c2;
-                const uint32_t dst = sRing + c2 * CHUNK_BYTES;
+            for (int hf = 0; hf < 2; ++hf) {                         // 16 hidden columns at a time (register budget)
+                const int n0 = j * 32 + hf * 16;
+                uint32_t rh[16], rd[16];
+                tmem_ld16_nowait(tmem_base + (uint32_t)n0 + ((uint32_t)(lq * 32) << 16), rh);
+                tmem_ld16_nowait(tmem_base + T_DA + (uint32_t)((G & 1) * 64 + grp * 32 + hf * 16) + ((uint32_t)(lq * 32) << 16), rd);
+                tmem_wait_ld();
+                const uint32_t pair0 = (uint32_t)(((unsigned long long)row * HID + (unsigned long long)n0) >> 1);
+                if (hf == 0) mbar_wait(hid_empty(grp), (uint32_t)(((cj >> 1) & 1) ^ 1));      // tensor pipe and TMA have read the previous occupants
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {                     // 16 hidden columns at a time (register budget)
-                    const int n0 = q * 64 + c2 * 32 + hf * 16;
-                    uint32_t rh[16], rd[16];
-                    tmem_ld16_nowait(tmem_base + (uint32_t)n0 + ((uint32_t)(lq * 32) << 16), rh);
-                    tmem_ld16_nowait(tmem_base + T_DA + (uint32_t)(grp * 64 + c2 * 32 + hf * 16) + ((uint32_t)(lq * 32) << 16), rd);
-                    tmem_wait_ld();
-                    float av[16], dv[16];
-                    const uint32_t pair0 = (uint32_t)(((unsigned long long)row * HID + (unsigned long long)n0) >> 1);
+                for (int o8 = 0; o8 < 2; ++o8) {                     // 8 columns at a time from registers to the rings: no spill (L1 is all shared memory)
+                    float av[8], dv[8];
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
+                    for (int p = 0; p < 4; ++p) {
+                        const int e = 8 * o8 + 2 * p;
                         float d0 = 1.f, d1 = 1.f;
                         if (drop_on) {
-                            const uint32_t h = cmgan_mix32(((pair0 + (uint32_t)p) * 0x9E3779B1u) ^ seed1_32);
+                            const uint32_t h = cmgan_mix32(((pair0 + (uint32_t)(4 * o8 + p)) * 0x9E3779B1u) ^ seed1_32);
                             d0 = (h & 0xFFFFu) >= thr16 ? g.inv_keep : 0.f; d1 = (h >> 16) >= thr16 ? g.inv_keep : 0.f;
                         }
-                        const float h0 = __uint_as_float(rh[2 * p]) + b1s[n0 + 2 * p], h1 = __uint_as_float(rh[2 * p + 1]) + b1s[n0 + 2 * p + 1];
+                        const float h0 = __uint_as_float(rh[e]) + b1s[n0 + e], h1 = __uint_as_float(rh[e + 1]) + b1s[n0 + e + 1];
                         const float s0 = sigmoidf_(h0), s1 = sigmoidf_(h1);
                         av[2 * p] = to_tf32(h0 * s0 * d0);
                         av[2 * p + 1] = to_tf32(h1 * s1 * d1);
-                        dv[2 * p] = to_tf32(__uint_as_float(rd[2 * p]) * d0 * (s0 * (1.f + h0 * (1.f - s0))));
-                        dv[2 * p + 1] = to_tf32(__uint_as_float(rd[2 * p + 1]) * d1 * (s1 * (1.f + h1 * (1.f - s1))));
+                        dv[2 * p] = to_tf32(__uint_as_float(rd[e]) * d0 * (s0 * (1.f + h0 * (1.f - s0))));
+                        dv[2 * p + 1] = to_tf32(__uint_as_float(rd[e + 1]) * d1 * (s1 * (1.f + h1 * (1.f - s1))));
                     }
-                    // the ring first: mbarrier.arrive releases every earlier write of the thread, global ones included -- stores to HBM issued before it
-                    // would have to drain (MEMBAR) before the tensor pipe may see the chunk
-                    if (hf == 0) mbar_wait(hid_empty(c2), (uint32_t)(((cj >> 1) & 1) ^ 1));        // the third contraction has read the previous occupant
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) st_shared_v4(dst + sw_off(rloc, hf * 4 + c), dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
-                    if (hf == 1) {
-                        fence_proxy_async();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(hid_full(c2));
-                    }
-                    if (ok) {
-                        float4* ao = reinterpret_cast<float4*>(g.a_out + row * HID + n0);
-                        float4* go = reinterpret_cast<float4*>(g.dh_out + row * HID + n0);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            ao[c] = make_float4(av[4 * c], av[4 * c + 1], av[4 * c + 2], av[4 * c + 3]);
-                            go[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
-                        }
+                    for (int c = 0; c < 2; ++c) {
+                        st_shared_v4(dstD + sw_off(rloc, hf * 4 + o8 * 2 + c), dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+                        st_shared_v4(dstA + sw_off(rloc, hf * 4 + o8 * 2 + c), av[4 * c], av[4 * c + 1], av[4 * c + 2], av[4 * c + 3]);
                     }
                 }
-
             }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hid_full(grp));
+            FFN_STAMP(3 * (int)(cj >> 1) + 2);
         }
     } else {
-        // ================================ WG4: LayerNorm-backward epilogue ================================
-        // thread = row.  Two sweeps over the row in halves of 32 channels; dxn is simply re-read from TMEM (cheap) and x from L2, so only
-        // 2 x 32 values are live at a time.
-        const int lq = warp & 3, rloc = lq * 32 + lane;
-        float accg0 = 0.f, accg1 = 0.f, accb0 = 0.f, accb1 = 0.f;       // lane's share of dgamma / dbeta: channels lane and 32 + lane
+        // ================================ LayerNorm-backward epilogue (warps 16-23) ================================
+        // thread = half a row (32 channels), swept twice in pieces of 16 channels: dxn is simply re-read from TMEM and x from L2 (the warps
+        // have time to spare), so only 3 x 16 values are live.  The two halves of a row exchange their partial sums (sum g, sum g xhat)
+        // through shared memory around a 64-thread named barrier.
+        const int ew = warp - 16, lq = warp & 3, hv = ew >> 2, rloc = lq * 32 + lane;
+        float accg = 0.f, accb = 0.f;                           // dgamma / dbeta share of this lane (channel: see the end of the loop)
+        auto reduce16 = [&](float v[16]) {                      // column sums over the warp's 32 rows: afterwards v[0] = total of entry lane >> 1
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool up = lane & 16;
+                const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool up = lane & 8;
+                const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool up = lane & 4;
+                const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+                const bool up = lane & 2;
+                const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+                v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        };
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int buf = lt & 1;
             const long row = ((long)blockIdx.x + (long)lt * gridDim.x) * BM + rloc;
             const bool ok = row < g.M;
-            const float4* xr = reinterpret_cast<const float4*>(g.x + (ok ? row : 0) * g.ldx);
+            const float4* xr = reinterpret_cast<const float4*>(g.x + (ok ? row : 0) * g.ldx) + hv * 8;
+            float4 xv[8];                                        // first sweep's x: requested before the accumulator is ready
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) xv[c4] = ok ? __ldg(xr + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            FFN_STAMP(3 * lt);
             mbar_wait(acc_full(buf), (uint32_t)((lt >> 1) & 1));
+            FFN_STAMP(3 * lt + 1);
             tc_fence_after();
             const float2 st = stat[(lt & 1) * BM + rloc];
-            const uint32_t taddr = tmem_base + T_ACC + (uint32_t)(buf * 64) + ((uint32_t)(lq * 32) << 16);
+            const uint32_t taddr = tmem_base + T_ACC + (uint32_t)(buf * 64 + hv * 32) + ((uint32_t)(lq * 32) << 16);
             float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-            for (int hv = 0; hv < 2; ++hv) {
-                float r[32];
-                tmem_ld16f_nowait(taddr + hv * 32, r); tmem_ld16f_nowait(taddr + hv * 32 + 16, r + 16);
-                float4 xv[8];
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) xv[c4] = __ldg(xr + hv * 8 + c4);
+            for (int pc = 0; pc < 2; ++pc) {
+                float r[16];
+                tmem_ld16f_nowait(taddr + pc * 16, r);
                 tmem_wait_ld();
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float xs[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 t = xv[pc * 4 + c4];
+                    const float xs[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float gk = r[4 * c4 + j] * gam[32 * hv + 4 * c4 + j];
+                        const float gk = r[4 * c4 + j] * gam[32 * hv + 16 * pc + 4 * c4 + j];
                         c1 += gk; c2 = fmaf(gk, (xs[j] - st.x) * st.y, c2);
                     }
                 }
             }
             if (!ok) { c1 = 0.f; c2 = 0.f; }
-            c1 *= (1.f / 64.f); c2 *= (1.f / 64.f);
+            exch[((lt & 1) * 2 + hv) * BM + rloc] = make_float2(c1, c2);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + lq) : "memory");          // the two warps that share these 32 rows
+            const float2 oth = exch[((lt & 1) * 2 + (hv ^ 1)) * BM + rloc];
+            c1 = (c1 + oth.x) * (1.f / 64.f); c2 = (c2 + oth.y) * (1.f / 64.f);
 #pragma unroll
-            for (int hv = 0; hv < 2; ++hv) {
-                float r[32], xh[32];
-                tmem_ld16f_nowait(taddr + hv * 32, r); tmem_ld16f_nowait(taddr + hv * 32 + 16, r + 16);
+            for (int pc = 0; pc < 2; ++pc) {
+                float r[16], xh[16];
+                tmem_ld16f_nowait(taddr + pc * 16, r);
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 t = __ldg(xr + hv * 8 + c4);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 t = ok ? __ldg(xr + pc * 4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     xh[4 * c4] = (t.x - st.x) * st.y; xh[4 * c4 + 1] = (t.y - st.x) * st.y; xh[4 * c4 + 2] = (t.z - st.x) * st.y; xh[4 * c4 + 3] = (t.w - st.x) * st.y;
                 }
                 tmem_wait_ld();
-                if (hv == 1) {                                       // last TMEM read of this accumulator
+                if (pc == 1) {                                       // last read of this accumulator (and of the tile's row statistics)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(buf));
                 }
                 if (ok) {
-                    const float4* dor = reinterpret_cast<const float4*>(g.dout + row * g.lddo) + hv * 8;
-                    const float4* r2 = g.res2 ? reinterpret_cast<const float4*>(g.res2 + row * g.ldr2) + hv * 8 : nullptr;
-                    float4* dxr = reinterpret_cast<float4*>(g.dx + row * g.lddx) + hv * 8;
+                    const float4* dor = reinterpret_cast<const float4*>(g.dout + row * g.lddo) + hv * 8 + pc * 4;
+                    const float4* r2 = g.res2 ? reinterpret_cast<const float4*>(g.res2 + row * g.ldr2) + hv * 8 + pc * 4 : nullptr;
+                    float4* dxr = reinterpret_cast<float4*>(g.dx + row * g.lddx) + hv * 8 + pc * 4;
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
+                    for (int c4 = 0; c4 < 4; ++c4) {
                         float4 o = __ldg(dor + c4);
                         if (r2) { const float4 e = __ldg(r2 + c4); o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
-                        const int k = 4 * c4, kg = 32 * hv + k;
+                        const int k = 4 * c4, kg = 32 * hv + 16 * pc + k;
                         o.x += st.y * (r[k + 0] * gam[kg + 0] - c1 - xh[k + 0] * c2);
                         o.y += st.y * (r[k + 1] * gam[kg + 1] - c1 - xh[k + 1] * c2);
                         o.z += st.y * (r[k + 2] * gam[kg + 2] - c1 - xh[k + 2] * c2);
@@ -675,15 +757,18 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { r[k] = ok ? r[k] : 0.f; xh[k] *= r[k]; }
-                warp_transpose_sum32(xh, lane);                      // dgamma: column sums of dxn * xhat
-                warp_transpose_sum32(r, lane);                       // dbeta:  column sums of dxn
-                if (hv == 0) { accg0 += xh[0]; accb0 += r[0]; } else { accg1 += xh[0]; accb1 += r[0]; }
+                for (int k = 0; k < 16; ++k) { r[k] = ok ? r[k] : 0.f; xh[k] *= r[k]; }
+                reduce16(xh);                                        // dgamma: column sums of dxn * xhat
+                reduce16(r);                                         // dbeta:  column sums of dxn
+                // every lane pair (2 c, 2 c + 1) now holds the totals of channel 32 hv + 16 pc + c: the even lane keeps piece 0's, the odd lane piece 1's
+                if ((lane & 1) == pc) { accg += xh[0]; accb += r[0]; }
             }
+            FFN_STAMP(3 * lt + 2);
         }
         if (my_tiles > 0) {
-            atomicAdd(g.dgamma + lane, accg0); atomicAdd(g.dgamma + 32 + lane, accg1);
-            atomicAdd(g.dbeta + lane, accb0); atomicAdd(g.dbeta + 32 + lane, accb1);
+            const int ch = 32 * hv + 16 * (lane & 1) + (lane >> 1);
+            atomicAdd(g.dgamma + ch, accg);
+            atomicAdd(g.dbeta + ch, accb);
         }
     }
     __syncthreads();
@@ -693,6 +778,22 @@ __global__ void __launch_bounds__(NT_BWD, 1) ffn_bwd_kernel(const __grid_constan
     }
 }
 
+long long* g_ffn_dbg = nullptr;
+
+using PFN_encodeTiled_ffn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled_ffn get_encoder_ffn() {
+    static PFN_encodeTiled_ffn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<PFN_encodeTiled_ffn>(fn);
+    }
+    return encode;
+}
 int g_sms = 0;
 int num_sms() {
     if (g_sms == 0) {
@@ -704,6 +805,9 @@ int num_sms() {
 }
 
 }  // namespace
+
+// developer aid: a device buffer of 32 warps x 64 clock64 stamps filled by CTA 0 of the next cmgan_ffn_fwd launches (nullptr switches it off)
+CMGAN_API int cmgan_ffn_debug_timeline(long long* buf) { g_ffn_dbg = buf; return 0; }
 
 // out = x + alpha * drop(seed2)( W2 ( swish(W1 LN(x) + b1) * drop(seed1) ) + b2 ).  W1p / W2p: the weights re-tiled by cmgan_pack_weights
 // (W1 (256, 64): sb_k = 1, sb_n = 64, N = 256, Cin = 64;  W2 (64, 256): sb_k = 1, sb_n = 256, N = 64, Cin = 256).  thr = p * 2^32 (0: no dropout).
@@ -724,6 +828,7 @@ CMGAN_API int cmgan_ffn_fwd(const float* x, long long ldx, long long M, const fl
     FfnFwdArgs a;
     a.x = x; a.ldx = ldx; a.out = out; a.ldo = ldo; a.ln_g = ln_g; a.ln_b = ln_b; a.W1p = W1p; a.b1 = b1; a.W2p = W2p; a.b2 = b2; a.M = M; a.alpha = alpha;
     a.seed1 = seed1; a.seed2 = seed2; a.thr = thr; a.inv_keep = inv_keep; a.seed_dev = seed_dev;
+    a.dbg = g_ffn_dbg;
     const int ntiles = (int)((M + BM - 1) / BM);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
     ffn_fwd_kernel<<<grid, NTHREADS, SMEM_FWD, (cudaStream_t)stream>>>(a);
@@ -743,6 +848,7 @@ CMGAN_API int cmgan_ffn_bwd(const float* x, long long ldx, const float* dz, long
     CMGAN_REQUIRE((((uintptr_t)x | (uintptr_t)dz | (uintptr_t)dout | (uintptr_t)res2 | (uintptr_t)dx | (uintptr_t)a_out | (uintptr_t)dh_out | (uintptr_t)xn_out) & 15) == 0,
                   "cmgan_ffn_bwd: rows must be 16-byte aligned");
     CMGAN_REQUIRE((((uintptr_t)W1p | (uintptr_t)W2tp | (uintptr_t)W1tp) & 127) == 0, "cmgan_ffn_bwd: weight images must be 128-byte aligned");
+    CMGAN_REQUIRE(M < (1ll << 31), "cmgan_ffn_bwd: too many rows");
     if (M == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -750,12 +856,26 @@ CMGAN_API int cmgan_ffn_bwd(const float* x, long long ldx, const float* dz, long
         if (e != cudaSuccess) { cmgan_set_error("cmgan_ffn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
         attr_set = true;
     }
+    // a / dh leave the kernel through TMA: (M, 256) row-major tensors, boxes of 128 rows x 32 floats in the SWIZZLE_128B shared-memory layout
+    PFN_encodeTiled_ffn encode = get_encoder_ffn();
+    CMGAN_REQUIRE(encode != nullptr, "cmgan_ffn_bwd: cuTensorMapEncodeTiled is not available from this driver");
+    alignas(64) CUtensorMap tmA, tmDh;
+    const cuuint64_t gdim[2] = {(cuuint64_t)HID, (cuuint64_t)M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)HID * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a_out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tmDh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dh_out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CMGAN_REQUIRE(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "cmgan_ffn_bwd: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
     FfnBwdArgs a;
     a.x = x; a.ldx = ldx; a.dz = dz; a.lddz = lddz; a.dout = dout; a.lddo = lddo; a.res2 = res2; a.ldr2 = ldr2; a.dx = dx; a.lddx = lddx;
-    a.a_out = a_out; a.dh_out = dh_out; a.xn_out = xn_out; a.ln_g = ln_g; a.ln_b = ln_b; a.b1 = b1; a.W1p = W1p; a.W2tp = W2tp; a.W1tp = W1tp;
+    a.xn_out = xn_out; a.ln_g = ln_g; a.ln_b = ln_b; a.b1 = b1; a.W1p = W1p; a.W2tp = W2tp; a.W1tp = W1tp;
     a.dgamma = dgamma; a.dbeta = dbeta; a.M = M; a.seed1 = seed1; a.thr = thr; a.inv_keep = inv_keep; a.seed_dev = seed_dev;
+    a.dbg = g_ffn_dbg;
     const int ntiles = (int)((M + BM - 1) / BM);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    ffn_bwd_kernel<<<grid, NT_BWD, SMEM_BWD, (cudaStream_t)stream>>>(a);
+    ffn_bwd_kernel<<<grid, NT_BWD, SMEM_BWD, (cudaStream_t)stream>>>(a, tmA, tmDh);
     return cmgan_check_launch("ffn_bwd_kernel");
 }

@@ -6,6 +6,7 @@ so that every launch reads its rows from HBM.  Prints one JSON line per configur
     python tools/bench_ffn.py [--batch 4] [--reps 40] [--profile]      (--profile: cudaProfilerStart/Stop around a few fused launches, for ncu)
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -24,6 +25,8 @@ def main():
     ap.add_argument("--reps", type=int, default=40)
     ap.add_argument("--drop", type=float, default=0.2)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--timeline-bwd", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="dump CTA 0's per-warp clock64 stamps of one fused forward launch")
     a = ap.parse_args()
     dev = "cuda"
     ops.set_precision("tf32")
@@ -100,6 +103,21 @@ def main():
         us = timeit(fn)
         res[name] = {"us": us, "tflops": bflop / us / 1e6, "io_gbs": bbytes / us / 1e3}
     print(json.dumps(res))
+    if a.timeline_bwd:
+        a.timeline = True
+    if a.timeline:
+        buf = torch.zeros(32 * 64, dtype=torch.int64, device=dev)
+        from cmgan_b200._lib import lib
+        lib().cdll.cmgan_ffn_debug_timeline(ctypes.c_void_p(buf.data_ptr()))
+        (fused_bwd if a.timeline_bwd else fused)(1)
+        torch.cuda.synchronize()
+        lib().cdll.cmgan_ffn_debug_timeline(None)
+        t = buf.view(32, 64).cpu()
+        t0 = int(t[t > 0].min())
+        for w in range(32):
+            row = [int(v) - t0 if v > 0 else -1 for v in t[w].tolist()]
+            if any(v >= 0 for v in row):
+                print("warp", w, row, file=sys.stderr)
     if a.profile:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
