@@ -395,7 +395,11 @@ def run_ours(args):
     if rank == 0:
         emit(out)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured graphs hold NCCL kernels: tearing the process group down underneath them can block, so leave together and at once
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def extras(args, out, trainer, model, dev, step_ms):

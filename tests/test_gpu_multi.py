@@ -41,7 +41,8 @@ def _worker(rank, world, port, gpath, dpath, out):
         m.load_state_dict(O.load_weights_npz(gpath), strict=True)
         d = cmgan_b200.Discriminator(16)
         d.load_state_dict(O.load_weights_npz(dpath), strict=True)
-        m, d = m.to(dev).eval(), d.to(dev).eval()
+        m, d = m.to(dev).eval(), d.to(dev).train()        # D in train mode (power iterations: with the un-iterated u / v of a fresh init the
+        # learnable sigmoid saturates and every D gradient is exactly zero); dropout off, so the ranks stay comparable
         t = FusedTrainer(m, d)
         g = torch.Generator().manual_seed(0)
         clean = 0.05 * torch.randn(4, 8000, generator=g)
@@ -69,6 +70,7 @@ def test_two_rank_gradients_equal_single_gpu_batch(tmp_path):
     # per utterance, BatchNorm runs on running statistics (eval), the spectral-norm power iteration is identical on both ranks
     for key, tol in (("gg", 2e-2), ("gd", 2e-2)):
         ref, got = b[key].double(), a[key].double()
+        assert ref.abs().max().item() > 0, f"{key}: reference gradient is identically zero"
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         print(f"[dp2] {key}: 2 x B=2 (all-reduce AVG) vs 1 x B=4: max-abs deviation / max {err:.3e}")
         assert np.isfinite(err) and err < tol, key
