@@ -224,9 +224,31 @@ class FusedTrainer:
         self.last = dict(clean_mag=clean_mag, est_mag=est_mag, est_audio=est_audio, B=B)
         return loss
 
-    def discriminator_step(self, pesq_target: torch.Tensor, update: bool = True) -> torch.Tensor:
-        """train.py:161-170,199-201 once the PESQ targets exist: MSE(D(c,c),1) + MSE(D(c, est.detach()), target)."""
-        d, L = self.disc, self.last
+    def train_step_async(self, clean: torch.Tensor, noisy: torch.Tensor, pesq) -> tuple:
+        """train.py:176-205 with the PESQ targets off the critical path (``pesq``: cmgan_b200.pesq_pipeline.AsyncPesq): generator step on
+        this batch, its waveforms handed to the host scorers, and the discriminator update for the PREVIOUS batch, whose scores had a whole
+        generator step to arrive (same clean / enhanced pair and targets as the reference's synchronous update, one step later; skipped
+        when any utterance of that batch failed to score).  Returns (generator loss, discriminator loss or None)."""
+        lg = self.generator_step(clean, noisy)
+        self._async_no = getattr(self, "_async_no", 0) + 1
+        n = self._async_no
+        pesq.submit(n, clean, self.last["est_audio"])
+        if not hasattr(self, "_await"):
+            self._await = {}
+        self._await[n] = self.last
+        ld = None
+        if n - 1 in self._await:
+            batch = self._await.pop(n - 1)
+            tgt = pesq.targets(n - 1, device=clean.device, wait=True)
+            pesq.forget(n - 1)
+            if tgt is not None:
+                ld = self.discriminator_step(tgt, batch=batch)
+        return lg, ld
+
+    def discriminator_step(self, pesq_target: torch.Tensor, update: bool = True, batch: Optional[dict] = None) -> torch.Tensor:
+        """train.py:161-170,199-201 once the PESQ targets exist: MSE(D(c,c),1) + MSE(D(c, est.detach()), target).  ``batch``: the
+        (clean_mag, est_mag) record of the generator step the targets belong to (default: the latest one)."""
+        d, L = self.disc, (self.last if batch is None else batch)
         dev = pesq_target.device
         ops.SEED_DEV = self.step_dev
         try:

@@ -147,3 +147,27 @@ def test_lr_schedule_under_graph_replay_and_checkpoint_roundtrip(g_weights, d_we
     sd = torch.load(ref_ck, map_location="cpu")
     assert len(sd) == 359
     cmgan_b200.TSCNet(64, 201).load_state_dict(sd, strict=True)
+
+
+def test_async_pesq_training_steps(g_weights, d_weights, golden):
+    """train_step_async: the discriminator update of batch n happens during step n + 1 with the targets the stand-in scorer gave batch n"""
+    from cmgan_b200.pesq_pipeline import AsyncPesq
+    m, d = _models(g_weights, d_weights)
+    m.train(); d.train()
+    t = FusedTrainer(m, d, lr=2e-4)
+    clean = torch.from_numpy(golden["grad_clean"]).to(DEV)
+    noisy = torch.from_numpy(golden["grad_noisy"]).to(DEV)
+    seen = []
+
+    def scorer(c, e):
+        seen.append((c.shape, e.shape))
+        return 1.0 + 3.5 * float(np.clip(1.0 - np.mean((c - e) ** 2) / (np.mean(c ** 2) + 1e-9), 0.0, 1.0))
+    p = AsyncPesq(scorer=scorer, workers=2)
+    pd0 = t.pd.clone()
+    lg, ld = t.train_step_async(clean, noisy, p)
+    assert ld is None and torch.equal(t.pd, pd0), "no discriminator update before the first batch has been scored"
+    out = [t.train_step_async(clean, noisy, p) for _ in range(3)]
+    assert all(np.isfinite(a.item()) and b is not None and np.isfinite(b.item()) for a, b in out)
+    assert not torch.equal(t.pd, pd0)
+    assert len(seen) >= 6 and seen[0][0] == seen[0][1] == (1600,)
+    p.close()
