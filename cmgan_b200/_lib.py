@@ -53,7 +53,7 @@ _CTYPE = {
 def parse_header(path: str = HEADER):
     """-> {name: (restype, [(ctype, argname), ...])} for every ``cmgan_*`` declaration."""
     protos = {}
-    pat = re.compile(r"^\s*(const char\*|int)\s+(cmgan_\w+)\((.*)\);\s*$")
+    pat = re.compile(r"^\s*(const char\*|int|long long)\s+(cmgan_\w+)\((.*)\);\s*$")
     with open(path) as fh:
         for line in fh:
             m = pat.match(line)
@@ -69,7 +69,7 @@ def parse_header(path: str = HEADER):
                     else:
                         ty, an = a.rsplit(" ", 1)
                         argl.append((_CTYPE[ty.strip()], an))
-            protos[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argl)
+            protos[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_longlong if ret == "long long" else ctypes.c_int, argl)
     return protos
 
 

@@ -146,6 +146,22 @@ def uncompress_istft(final_real: torch.Tensor, final_imag: torch.Tensor, c_div: 
 
 
 @torch.no_grad()
+def enhance_batch(model, noisy: torch.Tensor) -> torch.Tensor:
+    """(B, L) clips of ONE length, each treated exactly as ``enhance`` treats a single file no longer than cut_len (per-utterance RMS
+    normalisation, wrap padding, de-normalisation, truncation): the batched form used by the file front end and the throughput sweep."""
+    assert noisy.dim() == 2
+    noisy = noisy.contiguous()
+    B, length = noisy.shape
+    c = rms_scale(noisy)
+    padded_len = int(math.ceil(length / 100)) * 100
+    if padded_len != length:
+        noisy = torch.cat([noisy, noisy[:, :padded_len - length]], dim=-1)
+    spec = stft_compress(noisy, c).permute(0, 1, 3, 2)
+    fr, fi = model(spec)
+    return uncompress_istft(fr, fi, c)[:, :length]
+
+
+@torch.no_grad()
 def enhance(model, noisy: torch.Tensor, cut_len: int = 16000 * 16) -> torch.Tensor:
     """evaluation.enhance_one_track between load and save (ref: evaluation.py:21-53) on the GPU: (1, L) -> (L,)."""
     assert noisy.dim() == 2 and noisy.shape[0] == 1
