@@ -256,8 +256,15 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
          dbias=G[f"{p}.attn.fn.to_out.bias"])
     dqkv = _empty(M, 3 * C, dev=dev)
     delta = _empty(M, 4, dev=dev)
-    call("cmgan_attention_bwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_bwd", S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv,
-         G[f"{p}.attn.fn.rel_pos_emb.weight"])
+    attn_args = (S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv, G[f"{p}.attn.fn.rel_pos_emb.weight"])
+    if ops.PRECISION == 1 and ops.AUX_STREAM is not None and ops.PROBE is None:
+        # delta first; then the dq / dE kernel and the dk / dv kernel side by side (each alone leaves most of every SM idle)
+        call("cmgan_attention_bwd_tf32_parts", *attn_args, 1)
+        ops.call_on(ops.AUX_STREAM, "cmgan_attention_bwd_tf32_parts", *attn_args, 4)
+        call("cmgan_attention_bwd_tf32_parts", *attn_args, 2)
+        ops.join(ops.AUX_STREAM)
+    else:
+        call("cmgan_attention_bwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_bwd", *attn_args)
     dln2 = _empty(M, C, dev=dev)
     Wq, Wkv = P[f"{p}.attn.fn.to_q.weight"], P[f"{p}.attn.fn.to_kv.weight"]
     Gq, Gkv = G[f"{p}.attn.fn.to_q.weight"], G[f"{p}.attn.fn.to_kv.weight"]

@@ -38,6 +38,15 @@ __device__ __forceinline__ float tf32r(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// tf32 rounding of a finite value in one integer add: the tensor core ignores the low 13 mantissa bits, so adding half a tf32 ulp to the
+// bit pattern first makes that truncation a round-to-nearest (ties away from zero) -- cvt.rna.tf32.f32 costs five instructions here
+__device__ __forceinline__ float tf32q(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+// 2^x on the raw MUFU approximation (exp2f wraps it in range handling a softmax argument <= 0 does not need)
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void mma_tf32(float c[4], const float a[4], float b0, float b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
             const float mnew = fmaxf(mrun[hrow], m);
-            corr[hrow] = exp2f(mrun[hrow] - mnew);
+            corr[hrow] = ex2(mrun[hrow] - mnew);
             mrun[hrow] = mnew;
             lrun[hrow] *= corr[hrow];
         }
@@ -183,9 +192,9 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
             if (!FULL && nt >= ntv) continue;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const float p = exp2f(sc[nt][r] - mrun[r >> 1]);
+                const float p = ex2(sc[nt][r] - mrun[r >> 1]);
                 lrun[r >> 1] += p;
-                sc[nt][r] = tf32r(p);
+                sc[nt][r] = tf32q(p);
             }
         }
         // ---- O += P V.  k-step kk covers keys 8 kk .. 8 kk + 7; A-operand column t <-> key 2t, column t+4 <-> key 2t+1
@@ -230,6 +239,21 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
 //   p = exp2(s - lse),  dp = dO V^T,  ds = p (dp - delta),  delta_i = dO_i . O_i
 // (ds is the gradient wrt the natural-log logits; q is held pre-scaled by 0.25 log2(e), so sums against q take a final ln 2).
 constexpr float LN2 = 0.6931471805599453f;
+
+// ---- delta[row, h] = dO[row, h, :] . O[row, h, :]  (one thread per (row, head); lets the dq and dk/dv kernels run side by side)
+__global__ void attn_delta_kernel(const float* __restrict__ ctx, const float* __restrict__ dctx, long n, float* __restrict__ delta) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* o = reinterpret_cast<const float4*>(ctx + i * D);
+    const float4* d = reinterpret_cast<const float4*>(dctx + i * D);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 a = __ldg(o + k), b = __ldg(d + k);
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+    delta[i] = acc;
+}
 
 // ---- dq, delta and dE.  A block owns one 64-query tile position and walks over many (sequence, head) items, so the relative
 // distances it touches are the same for every item and dE can be accumulated in shared memory, flushed once at the end.
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
             if (row < g.L) {
                 const long rr = base + (long)row * g.tok_stride;
                 ls[hrow] = __ldg(lse + rr * H + h);
-                if (t == 0) delta[rr * H + h] = dl[hrow];
+                dl[hrow] = __ldg(delta + rr * H + h);          // written by attn_delta_kernel (the dk / dv kernel reads the same values)
             }
         }
         float dq[2][4];
@@ -366,9 +390,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                     for (int r = 0; r < 4; ++r) {
                         const int qrow = gq + (r >> 1) * 8, kcol = nt * 8 + 2 * t + (r & 1);
                         const float a = sc[nt][r] + R[qrow * LDRB + qrow - kcol + (KT - 1)];
-                        float ds = exp2f(a - ls[r >> 1]) * (dp[nt][r] - dl[r >> 1]);
+                        float ds = ex2(a - ls[r >> 1]) * (dp[nt][r] - dl[r >> 1]);
                         if (!FULL && kcol >= nk) ds = 0.f;
-                        sc[nt][r] = tf32r(ds);
+                        sc[nt][r] = tf32q(ds);
                     }
                 }
                 __syncwarp();
@@ -579,10 +603,10 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dkv_mma_kernel(const float* _
             for (int r = 0; r < 4; ++r) {
                 const int jl = warp * 16 + gq + (r >> 1) * 8, il = nt * 8 + 2 * t + (r & 1);
                 const float a = sc[nt][r] + R2[il * LDR2 + il - jl + (KT - 1)];
-                float p = exp2f(a - ((r & 1) ? l2.y : l2.x));
+                float p = ex2(a - ((r & 1) ? l2.y : l2.x));
                 if (!FULL && il >= nq) p = 0.f;          // queries past the end of the sequence (their lse was zero-filled)
-                sc[nt][r] = tf32r(p);
-                dp[nt][r] = tf32r(p * (dp[nt][r] - ((r & 1) ? d2.y : d2.x)));
+                sc[nt][r] = tf32q(p);
+                dp[nt][r] = tf32q(p * (dp[nt][r] - ((r & 1) ? d2.y : d2.x)));
             }
         }
         // ---- dV += P^T dO,  dK += dS^T Q   (A from the accumulator layout; queries of a k-step permuted)
@@ -636,9 +660,12 @@ CMGAN_API int cmgan_attention_fwd_tf32(const float* qkv, const float* E, int B, 
     return cmgan_check_launch("attn_fwd_mma_kernel");
 }
 
-// tf32 tensor-core backward (same contract as cmgan_attention_bwd: dqkv overwritten, dE accumulated, delta scratch)
-CMGAN_API int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
-                                       int T, int F, int axis, float* delta, float* dqkv, float* dE, void* stream) {
+// tf32 tensor-core backward (same contract as cmgan_attention_bwd: dqkv overwritten, dE accumulated, delta scratch).
+// parts: bit 0 = delta, bit 1 = dq + dE (reads delta), bit 2 = dk / dv (reads delta).  The two big kernels are independent of each other once
+// delta exists and each one alone leaves most of an SM idle (8 - 12 resident warps, barrier- and latency-bound), so the caller may run
+// part 1 first and then parts 2 and 4 on two streams; cmgan_attention_bwd_tf32 = all parts in order on one stream.
+CMGAN_API int cmgan_attention_bwd_tf32_parts(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
+                                             int T, int F, int axis, float* delta, float* dqkv, float* dE, int parts, void* stream) {
     CMGAN_REQUIRE(qkv && E && ctx && dctx && lse && delta && dqkv && dE, "cmgan_attention_bwd_tf32: null pointer");
     CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_attention_bwd_tf32: axis must be 0 (time) or 1 (freq)");
     SeqGeom g = make_seq_geom(B, T, F, axis);
@@ -664,8 +691,23 @@ CMGAN_API int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const f
     int ng = (148 * 2) / ntile;                      // one wave of 2 resident blocks per SM
     if (ng < 1) ng = 1;
     if (ng > n_items) ng = n_items;
-    attn_bwd_dq_mma_kernel<<<dim3(ng, ntile), 128, smem_dq, st>>>(qkv, g, E, ctx, dctx, lse, n_items, Lpad, delta, dqkv, dE);
-    if (cmgan_check_launch("attn_bwd_dq_mma_kernel")) return -1;
-    attn_bwd_dkv_mma_kernel<<<dim3(n_items, ntile), 128, smem_kv, st>>>(qkv, g, E, dctx, lse, delta, dqkv);
-    return cmgan_check_launch("attn_bwd_dkv_mma_kernel");
+    if (parts & 1) {
+        const long n = (long)B * T * F * H;
+        attn_delta_kernel<<<cdiv(n, 256), 256, 0, st>>>(ctx, dctx, n, delta);
+        if (cmgan_check_launch("attn_delta_kernel")) return -1;
+    }
+    if (parts & 2) {
+        attn_bwd_dq_mma_kernel<<<dim3(ng, ntile), 128, smem_dq, st>>>(qkv, g, E, ctx, dctx, lse, n_items, Lpad, delta, dqkv, dE);
+        if (cmgan_check_launch("attn_bwd_dq_mma_kernel")) return -1;
+    }
+    if (parts & 4) {
+        attn_bwd_dkv_mma_kernel<<<dim3(n_items, ntile), 128, smem_kv, st>>>(qkv, g, E, dctx, lse, delta, dqkv);
+        if (cmgan_check_launch("attn_bwd_dkv_mma_kernel")) return -1;
+    }
+    return 0;
+}
+
+CMGAN_API int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
+                                       int T, int F, int axis, float* delta, float* dqkv, float* dE, void* stream) {
+    return cmgan_attention_bwd_tf32_parts(qkv, E, ctx, dctx, lse, B, T, F, axis, delta, dqkv, dE, 7, stream);
 }

@@ -14,11 +14,12 @@ import torch
 from ._lib import GemmArgs, MAX_TAPS, lib
 
 # number of kernels each entry point launches (for bench.py's ``gpu_launches``)
-_KERNELS = {"cmgan_attention_bwd": 3, "cmgan_attention_bwd_tf32": 2}
+_KERNELS = {"cmgan_attention_bwd": 3, "cmgan_attention_bwd_tf32": 3}
 LAUNCHES = 0
 PRECISION = 1 if os.environ.get("CMGAN_PRECISION", "fp32").lower() == "tf32" else 0   # default for every dense contraction
 SEED_DEV = None  # optional uint64 device counter added to every dropout seed (set by the trainer for CUDA-graph replay)
 WGRAD_STREAM = None   # optional side stream: weight-gradient GEMMs run there, concurrently with the data-gradient chain (join_wgrad)
+AUX_STREAM = None     # optional second side stream: the dk / dv half of the attention backward runs there, next to the dq / dE half
 _WGRAD_KEEP = []      # operands of in-flight side-stream launches (kept allocated until the join)
 FUSED_FFN = os.environ.get("CMGAN_FUSED_FFN", "1") != "0"   # tf32 mode: one tcgen05 kernel per feed-forward module (csrc/ffn_fused.cu)
 PACK_CACHE = None   # optional PackCache: re-tiled tensor-core weight operands kept across calls (owner refreshes them after every weight update)
@@ -104,6 +105,26 @@ def packed_weight(W: "Ptr", sb_tap: int, sb_k: int, sb_n: int, Cin: int, ntaps: 
     dev = (W[0] if isinstance(W, tuple) else W).device
     cache = PACK_CACHE if PACK_CACHE is not None else PackCache()
     return cache.lookup(W, sb_tap, sb_k, sb_n, Cin, ntaps, N, dev)[0]
+
+
+def call_on(side: "torch.cuda.Stream", name: str, *args) -> None:
+    """``call`` on a side stream that first waits for everything enqueued so far on the current one (fork); pair with ``join``"""
+    global LAUNCHES
+    main = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    conv = [ptr(a) if (a is None or isinstance(a, (torch.Tensor, tuple))) else a for a in args]
+    lib().call(name, *conv, side.cuda_stream)
+    for a in args:
+        t = a[0] if isinstance(a, tuple) else a
+        if isinstance(t, torch.Tensor):
+            t.record_stream(side)
+    LAUNCHES += _KERNELS.get(name, 1)
+
+
+def join(side: "torch.cuda.Stream") -> None:
+    torch.cuda.current_stream().wait_stream(side)
 
 
 def join_wgrad() -> None:

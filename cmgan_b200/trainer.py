@@ -85,6 +85,8 @@ class FusedTrainer:
         self.model, self.disc, self.w = model, disc, weights
         if ops.WGRAD_STREAM is None and os.environ.get("CMGAN_WGRAD_STREAM", "1") != "0":
             ops.WGRAD_STREAM = torch.cuda.Stream()        # weight-gradient GEMMs overlap the data-gradient chain (also inside the CUDA graph)
+        if ops.AUX_STREAM is None and os.environ.get("CMGAN_AUX_STREAM", "1") != "0":
+            ops.AUX_STREAM = torch.cuda.Stream()          # the two halves of the attention backward run side by side
         self.pg = _flatten_params(model)
         self.gg = model.enable_flat_grads()
         self.opt_g = _Adam(self.pg, self.gg, lr)                      # train.py:63
