@@ -143,7 +143,7 @@ def conformer_fwd(x, P, p, B, T, F2, axis, training, seed, block_id, sums: _Sums
         gemm(A=xn2, lda=C, W=Wkv, sb_k=1, sb_n=C, C=(qkv, C), ldc=3 * C, M=M, N=2 * C, Cin=C)
     ctx = _empty(M, C, dev=dev)
     lse = _empty(M, 4, dev=dev)
-    call("cmgan_attention_fwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_fwd", qkv, P[f"{p}.attn.fn.rel_pos_emb.weight"], B, T, F2, axis,
+    call(("cmgan_attention_fwd_tc" if ops.ATTN_TC else "cmgan_attention_fwd_tf32") if ops.PRECISION == 1 else "cmgan_attention_fwd", qkv, P[f"{p}.attn.fn.rel_pos_emb.weight"], B, T, F2, axis,
          ctx, lse)
     x2 = _empty(M, C, dev=dev)
     gemm(A=ctx, lda=C, W=P[f"{p}.attn.fn.to_out.weight"], sb_k=1, sb_n=C, bias=P[f"{p}.attn.fn.to_out.bias"], C=x2, ldc=C, M=M, N=C, Cin=C,

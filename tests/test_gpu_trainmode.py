@@ -249,8 +249,9 @@ def _attn_ref64(qkv, E, B, T, F2, axis):
     return _rows_from_seq(out, B, T, F2, axis)
 
 
-@pytest.mark.parametrize("B,T,F2,axis", [(2, 321, 5, 0), (2, 7, 101, 1), (1, 641, 3, 0), (1, 1281, 2, 0)])
-def test_tc_attention_fwd_bwd_vs_float64(B, T, F2, axis):
+@pytest.mark.parametrize("fwd", ["cmgan_attention_fwd_tc", "cmgan_attention_fwd_tf32"])
+@pytest.mark.parametrize("B,T,F2,axis", [(2, 321, 5, 0), (2, 7, 101, 1), (1, 641, 3, 0), (1, 1281, 2, 0), (3, 130, 2, 0), (1, 2, 64, 1)])
+def test_tc_attention_fwd_bwd_vs_float64(B, T, F2, axis, fwd):
     """tensor-core attention forward and backward (dq, dk, dv, dE) directly vs float64 autograd, L = 321 / 101 / 641 / 1281"""
     M = B * T * F2
     qkv, E = _rand(M, 192, seed=7), _rand(1025, 16, seed=8, scale=0.5)
@@ -259,11 +260,11 @@ def test_tc_attention_fwd_bwd_vs_float64(B, T, F2, axis):
     ref = _attn_ref64(q64, E64, B, T, F2, axis)
     ref.backward(dctx.double())
     ctx, lse = torch.empty(M, 64, device=DEV), torch.empty(M, 4, device=DEV)
-    call("cmgan_attention_fwd_tf32", qkv, E, B, T, F2, axis, ctx, lse)
+    call(fwd, qkv, E, B, T, F2, axis, ctx, lse)
     dqkv, delta, dE = torch.empty(M, 192, device=DEV), torch.empty(M, 4, device=DEV), torch.zeros(1025, 16, device=DEV)
     call("cmgan_attention_bwd_tf32", qkv, E, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE)
     e_c, e_q, e_e = _rel(ctx, ref), _rel(dqkv, q64.grad), _rel(dE, E64.grad)
-    print(f"[tf32-vs-f64] attention B={B} T={T} F'={F2} axis={axis}: ctx {e_c:.3e}  dqkv {e_q:.3e}  dE {e_e:.3e}")
+    print(f"[tf32-vs-f64] attention ({fwd[16:]} forward) B={B} T={T} F'={F2} axis={axis}: ctx {e_c:.3e}  dqkv {e_q:.3e}  dE {e_e:.3e}")
     assert e_c <= 3e-3 and e_q <= 5e-3 and e_e <= 5e-3
 
 

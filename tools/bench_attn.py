@@ -39,6 +39,9 @@ def main():
         def fwd(i):
             call("cmgan_attention_fwd_tf32", qkvs[i % nb], E, B, T, F2, axis, ctx, lse)
 
+        def fwd_tc(i):
+            call("cmgan_attention_fwd_tc", qkvs[i % nb], E, B, T, F2, axis, ctx, lse)
+
         def bwd(i):
             call("cmgan_attention_bwd_tf32", qkvs[i % nb], E, ctx, dctxs[i % nb], lse, B, T, F2, axis, delta, dqkv, dE)
         side = torch.cuda.Stream()
@@ -49,7 +52,7 @@ def main():
             ops.call_on(side, "cmgan_attention_bwd_tf32_parts", *args, 4)
             call("cmgan_attention_bwd_tf32_parts", *args, 2)
             ops.join(side)
-        for fn, key in ((fwd, "fwd"), (bwd, "bwd"), (bwd2, "bwd_two_streams")):
+        for fn, key in ((fwd, "fwd"), (fwd_tc, "fwd_tc"), (bwd, "bwd"), (bwd2, "bwd_two_streams")):
             for i in range(3):
                 fn(i)
             torch.cuda.synchronize()
@@ -64,6 +67,7 @@ def main():
     print(json.dumps(res))
     if a.profile:
         torch.cuda.cudart().cudaProfilerStart()
+        call("cmgan_attention_fwd_tc", qkvs[0], E, B, T, F2, 0, ctx, lse)
         call("cmgan_attention_fwd_tf32", qkvs[0], E, B, T, F2, 0, ctx, lse)
         call("cmgan_attention_bwd_tf32", qkvs[0], E, ctx, dctxs[0], lse, B, T, F2, 0, delta, dqkv, dE)
         torch.cuda.synchronize()
