@@ -21,7 +21,10 @@ SEED_DEV = None  # optional uint64 device counter added to every dropout seed (s
 WGRAD_STREAM = None   # optional side stream: weight-gradient GEMMs run there, concurrently with the data-gradient chain (join_wgrad)
 AUX_STREAM = None     # optional second side stream: the dk / dv half of the attention backward runs there, next to the dq / dE half
 _WGRAD_KEEP = []      # operands of in-flight side-stream launches (kept allocated until the join)
-ATTN_TC = os.environ.get("CMGAN_ATTN_TC", "1") != "0"         # tf32 mode: attention forward on tcgen05 (csrc/attention_tc.cu) instead of mma.sync
+# tf32 mode: attention forward on tcgen05 (csrc/attention_tc.cu) instead of mma.sync.  Off by default: the first tcgen05 version is
+# parity-green but 18 % slower than the mma.sync kernel (377 vs 318 us, B = 4 time axis; profiles/README.md), its softmax warps wait on a
+# serial S/R -> softmax -> PV chain with one TMEM slot per CTA.
+ATTN_TC = os.environ.get("CMGAN_ATTN_TC", "0") != "0"
 FUSED_FFN = os.environ.get("CMGAN_FUSED_FFN", "1") != "0"   # tf32 mode: one tcgen05 kernel per feed-forward module (csrc/ffn_fused.cu)
 PACK_CACHE = None   # optional PackCache: re-tiled tensor-core weight operands kept across calls (owner refreshes them after every weight update)
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step
