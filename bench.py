@@ -271,6 +271,9 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    if args.global_batch:
+        assert args.global_batch % world == 0, "--global-batch must divide by the number of ranks"
+        args.batch = args.global_batch // world
     B = args.batch
     gd = args.workload == "train_gd"
     torch.manual_seed(0)
@@ -375,7 +378,8 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(B, args.workload), "global_batch": B * world, "clip_samples": CLIP, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations saved for backward, several GB) >> 126 MB L2; no explicit flush",
                        "weights": "torch.manual_seed(0) default init, updated by AdamW every step (lr 5e-4 / 1e-3)", "loss_after": loss_after,
@@ -588,6 +592,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU (configs[2]: 16; configs[3] = 8 per GPU on 8 GPUs)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total utterances split over the ranks (overrides --batch)")
     ap.add_argument("--workload", default="train_gd", choices=["train_gd", "gen_only"],
                     help="train_gd: generator + discriminator train step (configs[2], default); gen_only: generator step without the GAN term")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
