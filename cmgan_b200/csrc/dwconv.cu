@@ -1,146 +1,238 @@
 // GLU + depthwise Conv1d(k = 31, zero pad 15/15, bias) of the conformer convolution module.
 // Reference: conformer.py:30-48,164-168.  Input g (M, 256) = pointwise-conv output, u = g[:, :128] * sigmoid(g[:, 128:]),
 // out[tok, c] = bias[c] + sum_k w[c, k] * u[tok + k - 15, c] along the sequence axis (strided rows, SeqGeom).
-// HBM-bound: one pass over g, one write of out; the 31-tap window lives in shared memory (staged with 128-bit loads, all of a
-// tile's loads in flight before the first use).
+//
+// HBM-bound streaming kernels.  The (sequence, 16-token tile) space is flattened and cut into equal contiguous ranges, one per resident
+// block (persistent grid, no tail wave).  A block walks its range with a 64-row ring of staged rows in shared memory: every row of g
+// (and of dz) is read from global memory once and its sigmoid evaluated once -- no halo re-staging -- and the rows of tile k + 2 are
+// fetched into registers before tile k is computed, so the global-load latency hides under the FMA sweep.  Thread = (channel, 8-token
+// half of the tile); the taps (and the tap gradients) live in registers.
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 
 namespace {
 
-constexpr int CH = 128, KS = 31, PADL = 15, TT = 32, ROWS = TT + KS - 1;   // 62 staged rows per tile
-constexpr int C4 = CH / 4;
+constexpr int CH = 128, KS = 31, PADL = 15, C4 = CH / 4;
+constexpr int CK = 16;                 // rows per chunk = tokens per tile
+constexpr int RING = 64;               // ring rows: chunks k - 1, k, k + 1 are read while chunk k + 2 is written
+constexpr int TOK = 8;                 // tokens per thread per tile
+constexpr int SWEEP = TOK + KS - 1;    // 38 staged rows feed 8 consecutive tokens
 
-// U[r][c] = a * sigmoid(b) for tokens t0 - 15 + r;  SG (optional, TT rows) = sigmoid(b) of the centre rows
-__device__ __forceinline__ void stage_glu(float* U, float* SG, const float* __restrict__ g, long base, long tok_stride, int t0, int L) {
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < ROWS * C4; idx += blockDim.x) {
-        const int r = idx / C4, c4 = idx % C4;
-        const int tok = t0 - PADL + r;
-        float4 u = make_float4(0.f, 0.f, 0.f, 0.f), s = u;
+struct ChunkRegs {
+    float4 a[2], b[2], z[2];
+};
+
+// rows of chunk ch (tokens 16 ch .. 16 ch + 15) -> registers; rows outside the sequence read as zeros
+template <bool BWD>
+__device__ __forceinline__ void load_chunk(ChunkRegs& r, const float* __restrict__ g, const float* __restrict__ dz, long base, long tok_stride,
+                                           int ch, int L) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = threadIdx.x + 256 * j, row = idx >> 5, c4 = idx & 31;
+        const int tok = ch * CK + row;
+        r.a[j] = r.b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BWD) r.z[j] = r.a[j];
         if (tok >= 0 && tok < L) {
-            const float4* p = reinterpret_cast<const float4*>(g + (base + (long)tok * tok_stride) * (2 * CH));
-            const float4 a = __ldg(p + c4), b = __ldg(p + C4 + c4);
-            s = make_float4(sigmoidf_(b.x), sigmoidf_(b.y), sigmoidf_(b.z), sigmoidf_(b.w));
-            u = make_float4(a.x * s.x, a.y * s.y, a.z * s.z, a.w * s.w);
+            const long grow = base + (long)tok * tok_stride;
+            const float4* p = reinterpret_cast<const float4*>(g + grow * (2 * CH));
+            r.a[j] = __ldg(p + c4);
+            r.b[j] = __ldg(p + C4 + c4);
+            if (BWD) r.z[j] = __ldg(reinterpret_cast<const float4*>(dz + grow * CH) + c4);
         }
-        reinterpret_cast<float4*>(U)[idx] = u;
-        if (SG && r >= PADL && r < PADL + TT) reinterpret_cast<float4*>(SG)[(r - PADL) * C4 + c4] = s;
     }
 }
 
-__global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __restrict__ g, SeqGeom sg, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, float* __restrict__ out) {
-    __shared__ __align__(16) float U[ROWS * CH];
-    const int s = blockIdx.x, t0 = blockIdx.y * TT;
-    const long base = seq_base(sg, s);
-    stage_glu(U, nullptr, g, base, sg.tok_stride, t0, sg.L);
-    const int c = threadIdx.x % CH, half = threadIdx.x / CH;     // 2 halves x 16 tokens
+template <bool BWD>
+__device__ __forceinline__ void store_chunk(const ChunkRegs& r, float* U, float* SG, float* DZ, int ch) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = threadIdx.x + 256 * j, row = idx >> 5, c4 = idx & 31;
+        const int rr = (ch * CK + row) & (RING - 1);
+        const float4 a = r.a[j], b = r.b[j];
+        const float4 s = make_float4(sigmoidf_(b.x), sigmoidf_(b.y), sigmoidf_(b.z), sigmoidf_(b.w));
+        reinterpret_cast<float4*>(U)[rr * C4 + c4] = make_float4(a.x * s.x, a.y * s.y, a.z * s.z, a.w * s.w);
+        if (BWD) {
+            reinterpret_cast<float4*>(SG)[rr * C4 + c4] = s;
+            reinterpret_cast<float4*>(DZ)[rr * C4 + c4] = r.z[j];
+        }
+    }
+}
+
+// forward.  bn_sums (optional): per-channel sum / sum of squares of the output (sums[c * 2 + {0, 1}], BatchNorm1d batch statistics,
+// conformer.py:169) accumulated here instead of by a separate pass over `out`.
+__global__ void __launch_bounds__(256, 3) glu_dwconv_fwd_kernel(const float* __restrict__ g, SeqGeom sg, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ out,
+                                                                double* __restrict__ bn_sums) {
+    __shared__ __align__(16) float U[RING * CH];
+    const int c = threadIdx.x & (CH - 1), half = threadIdx.x >> 7;
     float wr[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) wr[k] = __ldg(w + c * KS + k);
-    const float b = __ldg(bias + c);
-    __syncthreads();
-#pragma unroll
-    for (int grp = 0; grp < 4; ++grp) {
-        const int tl = half * 16 + grp * 4;
-        float a0 = b, a1 = b, a2 = b, a3 = b;
-#pragma unroll
-        for (int m = 0; m < KS + 3; ++m) {
-            float u = U[(tl + m) * CH + c];
-            if (m < KS) a0 = fmaf(wr[m], u, a0);
-            if (m >= 1 && m - 1 < KS) a1 = fmaf(wr[m - 1], u, a1);
-            if (m >= 2 && m - 2 < KS) a2 = fmaf(wr[m - 2], u, a2);
-            if (m >= 3) a3 = fmaf(wr[m - 3], u, a3);
+    const float bs = __ldg(bias + c);
+    float s1 = 0.f, s2 = 0.f;
+    const int tps = (sg.L + CK - 1) / CK;
+    const long total = (long)sg.n_seq * tps;
+    long tile = total * blockIdx.x / gridDim.x;
+    const long hi = total * (blockIdx.x + 1) / gridDim.x;
+    ChunkRegs regs;
+    while (tile < hi) {
+        const int s = (int)(tile / tps), k0 = (int)(tile % tps);
+        const int kend = (int)min((long)tps, k0 + (hi - tile));
+        const long base = seq_base(sg, s);
+        __syncthreads();                                        // the previous run is done with the ring
+#pragma unroll 1
+        for (int ch = k0 - 1; ch <= k0 + 1; ++ch) {
+            load_chunk<false>(regs, g, nullptr, base, sg.tok_stride, ch, sg.L);
+            store_chunk<false>(regs, U, nullptr, nullptr, ch);
         }
-        float a[4] = {a0, a1, a2, a3};
+        __syncthreads();
+#pragma unroll 1
+        for (int k = k0; k < kend; ++k) {
+            load_chunk<false>(regs, g, nullptr, base, sg.tok_stride, k + 2, sg.L);
+            const int tok0 = k * CK + half * TOK;
+            const int rs = (tok0 - PADL) & (RING - 1), wm = RING - rs;          // sweep row m lives at ring row (rs + m) mod 64
+            const float* p1 = U + rs * CH + c;
+            const float* p2 = p1 - RING * CH;
+            float acc[TOK];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int tok = t0 + tl + q;
-            if (tok < sg.L) out[(base + (long)tok * sg.tok_stride) * CH + c] = a[q];
+            for (int i = 0; i < TOK; ++i) acc[i] = bs;
+#pragma unroll
+            for (int m = 0; m < SWEEP; ++m) {
+                const float u = (m < wm ? p1 : p2)[m * CH];
+#pragma unroll
+                for (int i = 0; i < TOK; ++i)
+                    if (m - i >= 0 && m - i < KS) acc[i] = fmaf(wr[m - i], u, acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < TOK; ++i) {
+                const int tok = tok0 + i;
+                if (tok < sg.L) {
+                    out[(base + (long)tok * sg.tok_stride) * CH + c] = acc[i];
+                    s1 += acc[i];
+                    s2 = fmaf(acc[i], acc[i], s2);
+                }
+            }
+            store_chunk<false>(regs, U, nullptr, nullptr, k + 2);
+            __syncthreads();
+        }
+        tile += kend - k0;
+    }
+    if (bn_sums) {
+        __syncthreads();
+        if (half) { U[c] = s1; U[CH + c] = s2; }
+        __syncthreads();
+        if (!half) {
+            atomicAdd(bn_sums + c * 2, (double)s1 + (double)U[c]);
+            atomicAdd(bn_sums + c * 2 + 1, (double)s2 + (double)U[CH + c]);
         }
     }
 }
 
 // backward.  dz = grad wrt out (M, 128).  dg (M, 256) overwritten; dw (128, 31), dbias (128) accumulated.
-__global__ void __launch_bounds__(256) glu_dwconv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ dz, SeqGeom sg,
-                                                             const float* __restrict__ w, int seqs_per_block, float* __restrict__ dg,
-                                                             float* __restrict__ dw, float* __restrict__ dbias, int rnd) {
+//   du[tok]  = sum_k w[k] dz[tok - k + 15]          dg_a = du sigmoid(b),  dg_b = du u (1 - sigmoid(b))
+//   dw[k]   += dz[tok] u[tok + k - 15]              dbias += dz[tok]
+__global__ void __launch_bounds__(256, 2) glu_dwconv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ dz, SeqGeom sg,
+                                                                const float* __restrict__ w, float* __restrict__ dg, float* __restrict__ dw,
+                                                                float* __restrict__ dbias, int rnd) {
     extern __shared__ __align__(16) float smem[];
-    float* U = smem;                    // [ROWS][CH]
-    float* DZ = smem + ROWS * CH;       // [ROWS][CH]
-    float* SG = DZ + ROWS * CH;         // [TT][CH]
-    const int c = threadIdx.x % CH, half = threadIdx.x / CH;
+    float* U = smem;                    // [RING][CH]
+    float* DZ = U + RING * CH;
+    float* SG = DZ + RING * CH;
+    const int c = threadIdx.x & (CH - 1), half = threadIdx.x >> 7;
     float wr[KS], dwr[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) { wr[k] = __ldg(w + c * KS + k); dwr[k] = 0.f; }
     float db = 0.f;
-    const int s_beg = blockIdx.x * seqs_per_block, s_end = min(s_beg + seqs_per_block, sg.n_seq);
-    for (int s = s_beg; s < s_end; ++s) {
+    const int tps = (sg.L + CK - 1) / CK;
+    const long total = (long)sg.n_seq * tps;
+    long tile = total * blockIdx.x / gridDim.x;
+    const long hi = total * (blockIdx.x + 1) / gridDim.x;
+    ChunkRegs regs;
+    while (tile < hi) {
+        const int s = (int)(tile / tps), k0 = (int)(tile % tps);
+        const int kend = (int)min((long)tps, k0 + (hi - tile));
         const long base = seq_base(sg, s);
-        for (int t0 = 0; t0 < sg.L; t0 += TT) {
-            __syncthreads();
-            stage_glu(U, SG, g, base, sg.tok_stride, t0, sg.L);
-#pragma unroll 4
-            for (int idx = threadIdx.x; idx < ROWS * C4; idx += blockDim.x) {
-                const int r = idx / C4, c4 = idx % C4;
-                const int tok = t0 - PADL + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tok >= 0 && tok < sg.L) v = __ldg(reinterpret_cast<const float4*>(dz + (base + (long)tok * sg.tok_stride) * CH) + c4);
-                reinterpret_cast<float4*>(DZ)[idx] = v;
-            }
-            __syncthreads();
-            // 4 consecutive tokens per pass share one sweep over the 34 staged rows they touch (68 shared-memory reads for 248 FMAs)
+        __syncthreads();
 #pragma unroll 1
-            for (int grp = 0; grp < 4; ++grp) {
-                const int tl = half * 16 + grp * 4;
-                if (t0 + tl >= sg.L) break;
-                float du[4] = {0.f, 0.f, 0.f, 0.f}, dzc[4];
+        for (int ch = k0 - 1; ch <= k0 + 1; ++ch) {
+            load_chunk<true>(regs, g, dz, base, sg.tok_stride, ch, sg.L);
+            store_chunk<true>(regs, U, SG, DZ, ch);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int k = k0; k < kend; ++k) {
+            load_chunk<true>(regs, g, dz, base, sg.tok_stride, k + 2, sg.L);
+            const int tok0 = k * CK + half * TOK;
+            const int rs = (tok0 - PADL) & (RING - 1), wm = RING - rs;
+            const int off1 = rs * CH + c, off2 = off1 - RING * CH;
+            float du[TOK], dzc[TOK];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { dzc[i] = DZ[(tl + i + PADL) * CH + c]; db += dzc[i]; }
-                // du[tok] = sum_k w[k] * dz[tok - k + 15]: staged row tl + m feeds token i with k = 30 - m + i
+            for (int i = 0; i < TOK; ++i) du[i] = 0.f;
+            // staged row m = token tok0 - 15 + m: feeds du of token i with tap k = 30 - m + i
 #pragma unroll
-                for (int m = 0; m < KS + 3; ++m) {
-                    const float z = DZ[(tl + m) * CH + c];
+            for (int m = 0; m < SWEEP; ++m) {
+                const float z = DZ[(m < wm ? off1 : off2) + m * CH];
+                if (m >= PADL && m < PADL + TOK) dzc[m - PADL] = z;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (m - i >= 0 && m - i < KS) du[i] = fmaf(wr[KS - 1 - m + i], z, du[i]);
-                }
-                // dw[k] += dz[tok] * u[tok + k - 15]: staged row tl + m feeds (token i, k = m - i)
+                for (int i = 0; i < TOK; ++i)
+                    if (m - i >= 0 && m - i < KS) du[i] = fmaf(wr[KS - 1 - m + i], z, du[i]);
+            }
 #pragma unroll
-                for (int m = 0; m < KS + 3; ++m) {
-                    const float u = U[(tl + m) * CH + c];
+            for (int i = 0; i < TOK; ++i) db += dzc[i];
+            // dw[k] += dz[token i] * u[row m],  k = m - i
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (m - i >= 0 && m - i < KS) dwr[m - i] = fmaf(dzc[i], u, dwr[m - i]);
-                }
+            for (int m = 0; m < SWEEP; ++m) {
+                const float u = U[(m < wm ? off1 : off2) + m * CH];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int tok = t0 + tl + i;
-                    if (tok >= sg.L) break;
-                    const long row = base + (long)tok * sg.tok_stride;
-                    const float sg_ = SG[(tl + i) * CH + c];
-                    const float u = U[(tl + i + PADL) * CH + c];            // a * sigmoid(b)
-                    dg[row * (2 * CH) + c] = cmgan_maybe_rna(du[i] * sg_, rnd);                    // dg feeds two tensor-core contractions
-                    dg[row * (2 * CH) + CH + c] = cmgan_maybe_rna(du[i] * u * (1.f - sg_), rnd);
+                for (int i = 0; i < TOK; ++i)
+                    if (m - i >= 0 && m - i < KS) dwr[m - i] = fmaf(dzc[i], u, dwr[m - i]);
+            }
+#pragma unroll
+            for (int i = 0; i < TOK; ++i) {
+                const int tok = tok0 + i;
+                if (tok < sg.L) {
+                    const int rr = (tok & (RING - 1)) * CH + c;
+                    const float sg_ = SG[rr], u = U[rr];
+                    float* o = dg + (base + (long)tok * sg.tok_stride) * (2 * CH) + c;
+                    o[0] = cmgan_maybe_rna(du[i] * sg_, rnd);                    // dg feeds two tensor-core contractions
+                    o[CH] = cmgan_maybe_rna(du[i] * u * (1.f - sg_), rnd);
                 }
             }
+            store_chunk<true>(regs, U, SG, DZ, k + 2);
+            __syncthreads();
         }
+        tile += kend - k0;
     }
+    // the two token halves of a channel are combined in shared memory: one atomic per (block, channel, tap)
+    __syncthreads();
+    if (half) {
 #pragma unroll
-    for (int k = 0; k < KS; ++k) atomicAdd(dw + c * KS + k, dwr[k]);
-    atomicAdd(dbias + c, db);
+        for (int k = 0; k < KS; ++k) U[k * CH + c] = dwr[k];
+        U[KS * CH + c] = db;
+    }
+    __syncthreads();
+    if (!half) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) atomicAdd(dw + c * KS + k, dwr[k] + U[k * CH + c]);
+        atomicAdd(dbias + c, db + U[KS * CH + c]);
+    }
+}
+
+int resident_grid(long total, int per_sm) {
+    const long slots = 148L * per_sm;
+    return (int)(total < slots ? total : slots);
 }
 
 }  // namespace
 
-CMGAN_API int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* bias, int B, int T, int F, int axis, float* out, void* stream) {
+CMGAN_API int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* bias, int B, int T, int F, int axis, float* out,
+                                   double* bn_sums, void* stream) {
     CMGAN_REQUIRE(g && w && bias && out && (((uintptr_t)g) & 15) == 0, "cmgan_glu_dwconv_fwd: bad pointer");
     CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_glu_dwconv_fwd: bad axis");
     SeqGeom sg = make_seq_geom(B, T, F, axis);
-    if (sg.n_seq == 0) return 0;
-    dim3 grid(sg.n_seq, cdiv(sg.L, TT));
-    glu_dwconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, sg, w, bias, out);
+    if (sg.n_seq == 0 || sg.L == 0) return 0;
+    const long total = (long)sg.n_seq * cdiv(sg.L, CK);
+    glu_dwconv_fwd_kernel<<<resident_grid(total, 3), 256, 0, (cudaStream_t)stream>>>(g, sg, w, bias, out, bn_sums);
     return cmgan_check_launch("glu_dwconv_fwd_kernel");
 }
 
@@ -149,17 +241,15 @@ CMGAN_API int cmgan_glu_dwconv_bwd(const float* g, const float* dz, const float*
     CMGAN_REQUIRE(g && dz && w && dg && dw && dbias && ((((uintptr_t)g) | ((uintptr_t)dz)) & 15) == 0, "cmgan_glu_dwconv_bwd: bad pointer");
     CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_glu_dwconv_bwd: bad axis");
     SeqGeom sg = make_seq_geom(B, T, F, axis);
-    if (sg.n_seq == 0) return 0;
+    if (sg.n_seq == 0 || sg.L == 0) return 0;
     static bool attr_set = false;
-    const int smem = (2 * ROWS + TT) * CH * (int)sizeof(float);
+    const int smem = 3 * RING * CH * (int)sizeof(float);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(glu_dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         CMGAN_REQUIRE(e == cudaSuccess, "cmgan_glu_dwconv_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    // enough blocks for ~4 waves of 148 SMs x 2 resident blocks, but at least one sequence per block
-    int spb = sg.n_seq / (148 * 2 * 4);
-    if (spb < 1) spb = 1;
-    glu_dwconv_bwd_kernel<<<cdiv(sg.n_seq, spb), 256, smem, (cudaStream_t)stream>>>(g, dz, sg, w, spb, dg, dw, dbias, g_cmgan_round_tf32);
+    const long total = (long)sg.n_seq * cdiv(sg.L, CK);
+    glu_dwconv_bwd_kernel<<<resident_grid(total, 2), 256, smem, (cudaStream_t)stream>>>(g, dz, sg, w, dg, dw, dbias, g_cmgan_round_tf32);
     return cmgan_check_launch("glu_dwconv_bwd_kernel");
 }

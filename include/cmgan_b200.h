@@ -58,7 +58,7 @@ int cmgan_attention_bwd_tf32_parts(const float* qkv, const float* E, const float
 int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B, int T, int F, int axis, float* delta, float* dqkv, float* dE, void* stream);
 
 /* ---- GLU + depthwise conv k=31 (conformer.py:30-48,164-168) */
-int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* bias, int B, int T, int F, int axis, float* out, void* stream);
+int cmgan_glu_dwconv_fwd(const float* g, const float* w, const float* bias, int B, int T, int F, int axis, float* out, double* bn_sums, void* stream);
 int cmgan_glu_dwconv_bwd(const float* g, const float* dz, const float* w, int B, int T, int F, int axis, float* dg, float* dw, float* dbias, void* stream);
 
 /* ---- signal front / back end (train.py:75-112, evaluation.py:21-51, utils.py:20-39) */

@@ -277,7 +277,8 @@ def test_attention_fwd_bwd(B, T, Fw, axis):
 
 
 # ------------------------------------------------------------------------------------------------ GLU + depthwise conv
-@pytest.mark.parametrize("B,T,Fw,axis", [(2, 45, 3, 0), (2, 3, 101, 1), (1, 20, 2, 0)])
+# the two large cases give every resident block a run of several tiles (ring wrap-around, range starts in mid-sequence)
+@pytest.mark.parametrize("B,T,Fw,axis", [(2, 45, 3, 0), (2, 3, 101, 1), (1, 20, 2, 0), (2, 321, 101, 0), (1, 161, 101, 1)])
 def test_glu_dwconv(B, T, Fw, axis):
     g = _rand(B, T, Fw, 256, seed=60).double().requires_grad_(True)
     w = (_rand(128, 1, 31, seed=61) * 0.2).double().requires_grad_(True)
@@ -293,8 +294,13 @@ def test_glu_dwconv(B, T, Fw, axis):
     gd = g.detach().float().view(-1, 256).to(DEV)
     wd, bd = w.detach().float().to(DEV), b.detach().float().to(DEV)
     out = torch.empty(M, 128, device=DEV)
-    call("cmgan_glu_dwconv_fwd", gd, wd, bd, B, T, Fw, axis, out)
+    sums = torch.zeros(128, 2, dtype=torch.float64, device=DEV)
+    call("cmgan_glu_dwconv_fwd", gd, wd, bd, B, T, Fw, axis, out, sums)
     _chk(out.view(B, T, Fw, 128), y, 5e-6, f"glu_dwconv fwd axis={axis}")
+    yf = y.detach().reshape(-1, 128)
+    _chk(sums[:, 0] / M, yf.mean(0), 5e-6, "glu_dwconv BatchNorm sum")
+    _chk(sums[:, 1] / M, (yf * yf).mean(0), 5e-6, "glu_dwconv BatchNorm sum of squares")
+    call("cmgan_glu_dwconv_fwd", gd, wd, bd, B, T, Fw, axis, out, None)          # eval path: no statistics
     dg, dw, db = torch.empty(M, 256, device=DEV), torch.zeros(128, 1, 31, device=DEV), torch.zeros(128, device=DEV)
     call("cmgan_glu_dwconv_bwd", gd, dz.view(-1, 128).to(DEV), wd, B, T, Fw, axis, dg, dw, db)
     _chk(dg.view(B, T, Fw, 256), g.grad, 1e-5, "glu_dwconv dg")
