@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--fwd-only", action="store_true")
+ap.add_argument("--gd", action="store_true", help="bench.py's default workload: generator step + discriminator step with both AdamW updates")
 ap.add_argument("--precision", default="tf32")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -25,7 +26,9 @@ _ops.set_precision(args.precision)
 torch.manual_seed(0)
 model = cmgan_b200.TSCNet(64, 201).to(dev).train()
 from cmgan_b200.trainer import FusedTrainer  # noqa: E402
-trainer = FusedTrainer(model, None)
+disc = cmgan_b200.Discriminator(16).to(dev).train() if args.gd else None
+trainer = FusedTrainer(model, disc)
+pesq_t = torch.full((args.batch,), 0.5, device=dev)
 clean, noisy = bench.synth_batch(args.batch, 1000, device=dev)
 
 
@@ -34,7 +37,11 @@ def step():
         with torch.no_grad():
             training.forward_generator_step(model, clean, noisy)
         return
-    trainer.generator_step(clean, noisy, update=False, allreduce=False)     # the step bench.py captures into its CUDA graph
+    if args.gd:                      # the step bench.py captures into its CUDA graph (configs[2])
+        trainer.generator_step(clean, noisy)
+        trainer.discriminator_step(pesq_t)
+        return
+    trainer.generator_step(clean, noisy, update=False, allreduce=False)
 
 
 for _ in range(args.warmup):
