@@ -163,6 +163,114 @@ __global__ void __launch_bounds__(NT, 2) gemm_wgrad_kernel(const __grid_constant
     if (do_bias && tid < WN && n0 + tid < g.N) atomicAdd(g.dbias + n0 + tid, bsum);
 }
 
+// narrow forward / data gradient: N <= 16 output columns (the discriminator's first convolution and its input gradient, the decoders'
+// 1- and 2-channel output convolutions).  Thread = one output row; the whole weight (ntaps * Cin x N, zero-padded to NP columns) sits in
+// shared memory and is read with broadcast 128-bit loads; A is read once, as it lies.
+template <int NP, int VEC>
+__global__ void __launch_bounds__(NT) gemm_rows_narrow_kernel(const __grid_constant__ CmganGemmArgs g) {
+    extern __shared__ __align__(16) float Ws[];           // [ntaps * Cin][NP]
+    const int ktot = g.ntaps * g.Cin;
+    for (int e = threadIdx.x; e < ktot * NP; e += NT) {
+        const int kk = e / NP, n = e - kk * NP;
+        const int tap = kk / g.Cin, k = kk - tap * g.Cin;
+        Ws[e] = n < g.N ? __ldg(g.B + (long)tap * g.sb_tap + (long)k * g.sb_k + (long)n * g.sb_n) : 0.f;
+    }
+    __syncthreads();
+    const long m = (long)blockIdx.x * NT + threadIdx.x;
+    if (m >= g.M) return;
+    const RowInfo ri = decode_row(g, (int)m);
+    float acc[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = (g.bias && n < g.N) ? __ldg(g.bias + n) : 0.f;
+    for (int tap = 0; tap < g.ntaps; ++tap) {
+        const long ir = in_row_of(g, ri, tap);
+        if (ir < 0) continue;
+        const float* ap = g.A + g.tap_off[tap] + ir * g.lda;
+        const float* wp = Ws + tap * g.Cin * NP;
+        for (int k = 0; k < g.Cin; k += VEC) {
+            float a[VEC];
+            if (VEC == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(ap + k));
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+            } else {
+                a[0] = __ldg(ap + k);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+#pragma unroll
+                for (int n4 = 0; n4 < NP; n4 += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(wp + (k + i) * NP + n4);
+                    acc[n4] = fmaf(a[i], w.x, acc[n4]); acc[n4 + 1] = fmaf(a[i], w.y, acc[n4 + 1]);
+                    acc[n4 + 2] = fmaf(a[i], w.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(a[i], w.w, acc[n4 + 3]);
+                }
+        }
+    }
+    float* cp = g.C + m * g.ldc;
+    if (NP == 16 && g.N == 16 && (g.ldc & 3) == 0 && (((uintptr_t)g.C) & 15) == 0) {
+#pragma unroll
+        for (int n4 = 0; n4 < 16; n4 += 4) *reinterpret_cast<float4*>(cp + n4) = make_float4(acc[n4], acc[n4 + 1], acc[n4 + 2], acc[n4 + 3]);
+    } else {
+#pragma unroll
+        for (int n = 0; n < NP; ++n)
+            if (n < g.N) cp[n] = acc[n];
+    }
+}
+
+// narrow weight gradient: few input channels x taps and few outputs (the discriminator's first convolution: 2 channels, 4 x 4 taps,
+// 16 outputs; the 64 x 64 tile above would be 99 % padding).  All ntaps * Cin <= 64 reduction columns and N <= 64 outputs of a row
+// chunk are accumulated by one block: thread = up to 16 (k, n) products, 32 gathered rows per stage.
+constexpr int NW_R = 32, NW_K = 64, NW_N = 64, NW_ACC = NW_K * NW_N / NT;
+__global__ void __launch_bounds__(NT) gemm_wgrad_narrow_kernel(const __grid_constant__ CmganGemmArgs g, int mch) {
+    __shared__ float As[NW_R][NW_K + 1];
+    __shared__ float Ds[NW_R][NW_N + 1];
+    const int tid = threadIdx.x;
+    const int ktot = g.ntaps * g.Cin, nout = ktot * g.N;
+    const long mbeg = (long)blockIdx.x * mch;
+    const long mend = mbeg + mch < g.M ? mbeg + mch : g.M;
+    float acc[NW_ACC];
+#pragma unroll
+    for (int j = 0; j < NW_ACC; ++j) acc[j] = 0.f;
+    for (long mb = mbeg; mb < mend; mb += NW_R) {
+        __syncthreads();
+        for (int e = tid; e < NW_R * ktot; e += NT) {
+            const int r = e / ktot, kk = e - r * ktot;
+            const int tap = kk / g.Cin, k = kk - tap * g.Cin;
+            const long m = mb + r;
+            float v = 0.f;
+            if (m < mend) {
+                const long ir = in_row_of(g, decode_row(g, (int)m), tap);
+                if (ir >= 0) v = __ldg(g.A + g.tap_off[tap] + ir * g.lda + k);
+            }
+            As[r][kk] = v;
+        }
+        for (int e = tid; e < NW_R * g.N; e += NT) {
+            const int r = e / g.N, n = e - r * g.N;
+            const long m = mb + r;
+            Ds[r][n] = m < mend ? __ldg(g.D + m * g.ldd + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NW_ACC; ++j) {
+            const int o = tid + NT * j;
+            if (o >= nout) break;
+            const int kk = o / g.N, n = o - kk * g.N;
+            float a = acc[j];
+#pragma unroll 8
+            for (int r = 0; r < NW_R; ++r) a = fmaf(As[r][kk], Ds[r][n], a);
+            acc[j] = a;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NW_ACC; ++j) {
+        const int o = tid + NT * j;
+        if (o >= nout) break;
+        const int kk = o / g.N, n = o - kk * g.N;
+        const int tap = kk / g.Cin, k = kk - tap * g.Cin;
+        atomicAdd(g.C + (long)tap * g.sb_tap + (long)k * g.sb_k + (long)n * g.sb_n, acc[j]);
+    }
+}
+
+
 bool vec_ok(const CmganGemmArgs& a) {
     if (a.lda % 4 || a.Cin % 4 || ((uintptr_t)a.A & 15)) return false;
     for (int t = 0; t < a.ntaps; ++t)
@@ -204,6 +312,20 @@ CMGAN_API int cmgan_gemm_rows_f32(const CmganGemmArgs* a, void* stream) {
         int rc = cmgan_gemm_rows_tc_launch(a, (cudaStream_t)stream);
         if (rc <= 0) return rc;
     }
+    if (a->N <= 16 && a->pro == CMGAN_PRO_NONE && a->epi == CMGAN_EPI_NONE && (long)a->ntaps * a->Cin * 16 * 4 <= 48 * 1024) {
+        const int np = a->N <= 4 ? 4 : 16;
+        const int smem = a->ntaps * a->Cin * np * (int)sizeof(float);
+        const unsigned grid_n = (unsigned)cdiv(a->M, NT);
+        const bool v4 = vec_ok(*a);
+        if (np == 4) {
+            if (v4) gemm_rows_narrow_kernel<4, 4><<<grid_n, NT, smem, (cudaStream_t)stream>>>(*a);
+            else gemm_rows_narrow_kernel<4, 1><<<grid_n, NT, smem, (cudaStream_t)stream>>>(*a);
+        } else {
+            if (v4) gemm_rows_narrow_kernel<16, 4><<<grid_n, NT, smem, (cudaStream_t)stream>>>(*a);
+            else gemm_rows_narrow_kernel<16, 1><<<grid_n, NT, smem, (cudaStream_t)stream>>>(*a);
+        }
+        return cmgan_check_launch("gemm_rows_narrow_kernel");
+    }
     dim3 grid(cdiv(a->M, BM), cdiv(a->N, BN));
     if (vec_ok(*a)) gemm_rows_kernel<4><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
     else gemm_rows_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);
@@ -218,6 +340,12 @@ CMGAN_API int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream) {
     if (a->precision == 1) {                       // tf32 tcgen05 path (gemm_wgrad_tc.cu); 1 = shape not covered -> exact fp32 path below
         int rc = cmgan_gemm_wgrad_tc_launch(a, (cudaStream_t)stream);
         if (rc <= 0) return rc;
+    }
+    if (a->ntaps * a->Cin <= NW_K && a->N <= NW_N && a->Cin < 16 && a->pro == CMGAN_PRO_NONE && a->prod == 0 && a->dbias == nullptr) {
+        long mch = cdiv(a->M, 148L * 4);
+        mch = cdiv(mch < 256 ? 256 : mch, NW_R) * NW_R;
+        gemm_wgrad_narrow_kernel<<<(unsigned)cdiv(a->M, mch), NT, 0, (cudaStream_t)stream>>>(*a, (int)mch);
+        return cmgan_check_launch("gemm_wgrad_narrow_kernel");
     }
     dim3 grid(cdiv(a->Cin, WK) * a->ntaps, cdiv(a->N, WN), cdiv(a->M, MCH));
     if (vec_ok(*a)) gemm_wgrad_kernel<4><<<grid, NT, 0, (cudaStream_t)stream>>>(*a);

@@ -121,18 +121,42 @@ __global__ void spectral_norm_kernel(const float* __restrict__ W, int R, int Cc,
     if (threadIdx.x == 0) sigma_out[0] = sigma;
 }
 
-// dW_orig += (dW_sn - <dW_sn, W_sn> u v^T) / sigma
-__global__ void spectral_norm_bwd_kernel(const float* __restrict__ w_sn, const float* __restrict__ dw_sn, int R, int Cc,
-                                         const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ sigma,
-                                         float* __restrict__ dW) {
+// dW_orig += (dW_sn - <dW_sn, W_sn> u v^T) / sigma.  One block (the dot product is a block-wide reduction over <= 131 k elements):
+// 1024 threads, 128-bit loads when the row length allows (every layer of the reference discriminator: Cc = 32 .. 1024).
+__global__ void __launch_bounds__(1024) spectral_norm_bwd_kernel(const float* __restrict__ w_sn, const float* __restrict__ dw_sn, int R, int Cc,
+                                                                 const float* __restrict__ u, const float* __restrict__ v,
+                                                                 const float* __restrict__ sigma, float* __restrict__ dW) {
     __shared__ float sm[32];
+    const long n = (long)R * Cc;
+    const bool v4 = (Cc & 3) == 0 && ((((uintptr_t)w_sn) | ((uintptr_t)dw_sn) | ((uintptr_t)dW) | ((uintptr_t)v)) & 15) == 0;
     float part = 0.f;
-    for (long k = threadIdx.x; k < (long)R * Cc; k += blockDim.x) part = fmaf(__ldg(dw_sn + k), __ldg(w_sn + k), part);
-    float dot = block_sum(part, sm);
-    float inv = 1.f / sigma[0];
-    for (long k = threadIdx.x; k < (long)R * Cc; k += blockDim.x) {
-        int i = (int)(k / Cc), j = (int)(k % Cc);
-        dW[k] += (__ldg(dw_sn + k) - dot * u[i] * v[j]) * inv;
+    if (v4) {
+#pragma unroll 4
+        for (long k = threadIdx.x; k < n / 4; k += blockDim.x) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(dw_sn) + k), b = __ldg(reinterpret_cast<const float4*>(w_sn) + k);
+            part += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+    } else {
+        for (long k = threadIdx.x; k < n; k += blockDim.x) part = fmaf(__ldg(dw_sn + k), __ldg(w_sn + k), part);
+    }
+    const float dot = block_sum(part, sm);
+    const float inv = 1.f / sigma[0];
+    if (v4) {
+        const int c4 = Cc / 4;
+#pragma unroll 4
+        for (long k = threadIdx.x; k < n / 4; k += blockDim.x) {
+            const int i = (int)(k / c4), j = (int)(k % c4);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(dw_sn) + k), vv = __ldg(reinterpret_cast<const float4*>(v) + j);
+            const float du = dot * u[i];
+            float4 o = reinterpret_cast<float4*>(dW)[k];
+            o.x += (a.x - du * vv.x) * inv; o.y += (a.y - du * vv.y) * inv; o.z += (a.z - du * vv.z) * inv; o.w += (a.w - du * vv.w) * inv;
+            reinterpret_cast<float4*>(dW)[k] = o;
+        }
+    } else {
+        for (long k = threadIdx.x; k < n; k += blockDim.x) {
+            const int i = (int)(k / Cc), j = (int)(k % Cc);
+            dW[k] += (__ldg(dw_sn + k) - dot * u[i] * v[j]) * inv;
+        }
     }
 }
 
@@ -244,7 +268,7 @@ CMGAN_API int cmgan_spectral_norm(const float* W, int R, int Cc, float* u, float
 CMGAN_API int cmgan_spectral_norm_bwd(const float* w_sn, const float* dw_sn, int R, int Cc, const float* u, const float* v, const float* sigma,
                                       float* dW, void* stream) {
     CMGAN_REQUIRE(w_sn && dw_sn && u && v && sigma && dW, "cmgan_spectral_norm_bwd: null pointer");
-    spectral_norm_bwd_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(w_sn, dw_sn, R, Cc, u, v, sigma, dW);
+    spectral_norm_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w_sn, dw_sn, R, Cc, u, v, sigma, dW);
     return cmgan_check_launch("spectral_norm_bwd_kernel");
 }
 

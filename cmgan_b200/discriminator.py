@@ -134,6 +134,7 @@ def disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
 
 def _disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
     dev = dout.device
+    need_w = G is not None         # generator step: only the input gradient is wanted -- no weight gradients, no spectral-norm backward
     if G is None:
         G = _Sink(P)
     B, H, W = S["x_shape"]
@@ -142,17 +143,20 @@ def _disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
     n1, n0 = S["w14"].shape
     dh2 = _empty(B, 1, dev=dev)
     call("cmgan_lsigmoid_bwd", S["h2"], S["out"], dout, B, P["layers.18.slope"], dh2, G["layers.18.slope"])
-    dw17 = torch.zeros_like(S["w17"])
-    gemm(wgrad=True, A=S["a1"], lda=n1, Cin=n1, D=dh2, ldd=1, N=1, W=None, C=dw17, sb_k=1, sb_n=n1, ldc=0, M=B, dbias=G["layers.17.bias"], precision=0)
-    _sn_bwd(P, G, "layers.17", S["w17"], dw17, S["s17"])
+    if need_w:
+        dw17 = torch.zeros_like(S["w17"])
+        gemm(wgrad=True, A=S["a1"], lda=n1, Cin=n1, D=dh2, ldd=1, N=1, W=None, C=dw17, sb_k=1, sb_n=n1, ldc=0, M=B, dbias=G["layers.17.bias"],
+             precision=0)
+        _sn_bwd(P, G, "layers.17", S["w17"], dw17, S["s17"])
     da1 = _empty(B, n1, dev=dev)
     gemm(A=dh2, lda=1, W=S["w17"], sb_k=n1, sb_n=1, C=da1, ldc=n1, M=B, N=n1, Cin=1, precision=0)
     dh1 = _empty(B, n1, dev=dev)
     call("cmgan_drop_prelu_bwd", S["h1"], da1, B * n1, n1, P["layers.16.weight"], S["seed"], S["thr"], S["inv"], dh1, G["layers.16.weight"], ops.SEED_DEV)
-    dw14 = torch.zeros_like(S["w14"])
-    gemm(wgrad=True, A=S["pooled"], lda=n0, Cin=n0, D=dh1, ldd=n1, N=n1, W=None, C=dw14, sb_k=1, sb_n=n0, ldc=0, M=B, dbias=G["layers.14.bias"],
-         precision=0)
-    _sn_bwd(P, G, "layers.14", S["w14"], dw14, S["s14"])
+    if need_w:
+        dw14 = torch.zeros_like(S["w14"])
+        gemm(wgrad=True, A=S["pooled"], lda=n0, Cin=n0, D=dh1, ldd=n1, N=n1, W=None, C=dw14, sb_k=1, sb_n=n0, ldc=0, M=B, dbias=G["layers.14.bias"],
+             precision=0)
+        _sn_bwd(P, G, "layers.14", S["w14"], dw14, S["s14"])
     dpool = _empty(B, n0, dev=dev)
     gemm(A=dh1, lda=n1, W=S["w14"], sb_k=n0, sb_n=1, C=dpool, ldc=n0, M=B, N=n0, Cin=n1, precision=0)
     # ---- conv stack in reverse
@@ -168,10 +172,11 @@ def _disc_bwd(S, dout, P, G, need_dx: bool, need_dy: bool):
         _norm_bwd(L["raw"], Cout, dact, Cout, B, oh * ow, Cout, 1, True, L["tab"], 0, P[f"layers.{idx + 2}.weight"], draw, Cout,
                   G[f"layers.{idx + 1}.weight"], G[f"layers.{idx + 1}.bias"], G[f"layers.{idx + 2}.weight"], sums, operand=True)
         conv = dict(OH=oh, OW=ow, IH=ih, IW=iw, mul_y=2, mul_x=2)
-        dw_sn = torch.zeros_like(L["w_sn"])
-        gemm(wgrad=True, A=L["a_in"], lda=Cin, Cin=Cin, taps=_TAPS, conv=conv, D=draw, ldd=Cout, N=Cout, W=None, C=dw_sn, sb_tap=1, sb_k=16,
-             sb_n=Cin * 16, ldc=0, M=M)
-        _sn_bwd(P, G, L["key"], L["w_sn"], dw_sn, L["sigma"])
+        if need_w:
+            dw_sn = torch.zeros_like(L["w_sn"])
+            gemm(wgrad=True, A=L["a_in"], lda=Cin, Cin=Cin, taps=_TAPS, conv=conv, D=draw, ldd=Cout, N=Cout, W=None, C=dw_sn, sb_tap=1, sb_k=16,
+                 sb_n=Cin * 16, ldc=0, M=M)
+            _sn_bwd(P, G, L["key"], L["w_sn"], dw_sn, L["sigma"])
         if li > 0 or need_dx or need_dy:
             Min = B * ih * iw
             dact = _empty(Min, Cin, dev=dev)
