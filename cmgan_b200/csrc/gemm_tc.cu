@@ -605,6 +605,14 @@ int cmgan_gemm_rows_tc_launch(const CmganGemmArgs* a, cudaStream_t st) {
 
 // Re-tile n weights (device table of CmganPackDesc) for the tensor-core path in one launch: called once after the optimiser step, so that the
 // GEMM launches of the next step find their B operand ready (CmganGemmArgs.b_packed = 1).
+// one weight -> its K-major SWIZZLE_128B tile image (the layout cmgan_ffn_fwd / the b_packed GEMM path consume): N * Cin * ntaps floats
+CMGAN_API int cmgan_pack_weight(const float* src, float* dst, long long sb_tap, long long sb_k, long long sb_n, int Cin, int ntaps, int N, void* stream) {
+    CMGAN_REQUIRE(src && dst && Cin > 0 && Cin % KC == 0 && ntaps >= 1 && N > 0, "cmgan_pack_weight: bad arguments (Cin must be a multiple of %d)", KC);
+    const long total = (long)ntaps * Cin * N;
+    pack_b_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, sb_tap, sb_k, sb_n, Cin, ntaps, N, N, dst);
+    return cmgan_check_launch("pack_b_kernel");
+}
+
 CMGAN_API int cmgan_pack_weights(const CmganPackDesc* descs, int n, void* stream) {
     CMGAN_REQUIRE(descs || n == 0, "cmgan_pack_weights: null table");
     if (n == 0) return 0;

@@ -23,80 +23,112 @@ __global__ void ln_stats_kernel(const float* __restrict__ x, long ldx, long M, f
     if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + EPS));
 }
 
+// Both LayerNorm kernels: a row (64 channels) is held by HALF a warp as one float4 per lane, so every instruction covers two rows and a
+// reduction is 4 shuffle steps; a warp walks LN_RPW consecutive rows with the per-channel parameters hoisted.  (The one-warp-per-row
+// float2 form was issue-bound: 112 instructions per 256-byte row, 72 % issue-slot utilisation at 1.5 TB/s.)
+constexpr int LN_RPW = 8;          // rows per warp (4 iterations of 2 rows)
+
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // y = LN(x) * gamma + beta (+ res);  stats written for the backward pass
-__global__ void ln_apply_kernel(const float* __restrict__ x, long ldx, long M, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ res, long ldr,
-                                float* __restrict__ y, long ldy, float2* __restrict__ stats, int round_tf32) {
-    long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (row >= M) return;
-    float2 v = __ldg(reinterpret_cast<const float2*>(x + row * ldx) + lane);
-    float mean = warp_sum(v.x + v.y) * (1.0f / LN_C);
-    float d0 = v.x - mean, d1 = v.y - mean;
-    float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / LN_C);
-    float rstd = rsqrtf(var + EPS);
-    float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + lane);
-    float2 b = __ldg(reinterpret_cast<const float2*>(beta) + lane);
-    float2 o = make_float2(d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y);
-    if (res) { float2 r = __ldg(reinterpret_cast<const float2*>(res + row * ldr) + lane); o.x += r.x; o.y += r.y; }
-    if (round_tf32) {      // consumer is a tf32 tensor-core GEMM fed by cp.async: round (not truncate) once, here
-        uint32_t a, b;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(o.x));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(o.y));
-        o = make_float2(__uint_as_float(a), __uint_as_float(b));
+__global__ void __launch_bounds__(256) ln_apply_kernel(const float* __restrict__ x, long ldx, long M, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ res, long ldr,
+                                                       float* __restrict__ y, long ldy, float2* __restrict__ stats, int round_tf32) {
+    const int lane = threadIdx.x & 31, hl = lane & 15, hw = lane >> 4;
+    const long r0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LN_RPW + hw;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + hl);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + hl);
+#pragma unroll
+    for (int it = 0; it < LN_RPW / 2; ++it) {
+        const long row = r0 + 2 * it;
+        const bool ok = row < M;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), r = v;
+        if (ok) {
+            v = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + hl);
+            if (res) r = __ldg(reinterpret_cast<const float4*>(res + row * ldr) + hl);
+        }
+        const float mean = half_warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / LN_C);
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        const float var = half_warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) * (1.0f / LN_C);
+        const float rstd = rsqrtf(var + EPS);
+        float4 o = make_float4(fmaf(d0 * rstd, g.x, b.x) + r.x, fmaf(d1 * rstd, g.y, b.y) + r.y, fmaf(d2 * rstd, g.z, b.z) + r.z,
+                               fmaf(d3 * rstd, g.w, b.w) + r.w);
+        if (round_tf32) {      // consumer is a tf32 tensor-core GEMM fed by TMA / cp.async: round (not truncate) once, here
+            o.x = cmgan_rna_tf32(o.x); o.y = cmgan_rna_tf32(o.y); o.z = cmgan_rna_tf32(o.z); o.w = cmgan_rna_tf32(o.w);
+        }
+        if (ok) {
+            reinterpret_cast<float4*>(y + row * ldy)[hl] = o;
+            if (stats && hl == 0) stats[row] = make_float2(mean, rstd);
+        }
     }
-    reinterpret_cast<float2*>(y + row * ldy)[lane] = o;
-    if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
 }
 
 // dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)) (+ res);  dgamma += sum dy*xhat;  dbeta += sum dy
-__global__ void ln_bwd_kernel(const float* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
                               const float2* __restrict__ stats, const float* __restrict__ gamma, long M,
                               const float* __restrict__ res, long ldr, const float* __restrict__ res2, long ldr2,
                               float* __restrict__ dx, long lddx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_warp,
                               float* __restrict__ dz, long lddz, float zalpha, unsigned long long zseed, unsigned zthr, float zinv_keep,
                               const unsigned long long* __restrict__ seed_dev, int rnd) {
-    __shared__ float sg[8][LN_C], sb[8][LN_C];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    long r0 = ((long)blockIdx.x * nw + warp) * rows_per_warp;
-    float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + lane);
-    float2 ag = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
+    __shared__ float4 sg[16][LN_C / 4], sb[16][LN_C / 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, hw = lane >> 4, nw = blockDim.x >> 5;
+    const long r0 = ((long)blockIdx.x * nw + warp) * rows_per_warp + hw;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + hl);
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
     // optional second output dz = zalpha * dropmask(zseed) * dx: the gradient entering the next residual branch, whose forward output
     // went through dropout (mask regenerated from the element index row * 64 + channel, as in the GEMM epilogue that applied it)
     const uint32_t zs32 = dz ? cmgan_seed32(cmgan_eff_seed(zseed, seed_dev)) : 0u;
     const uint32_t zt16 = zthr >> 16;
-    for (int i = 0; i < rows_per_warp; ++i) {
-        long row = r0 + i;
-        if (row >= M) break;
-        float2 v = __ldg(reinterpret_cast<const float2*>(x + row * ldx) + lane);
-        float2 d = __ldg(reinterpret_cast<const float2*>(dy + row * lddy) + lane);
-        float2 st = __ldg(stats + row);
-        float xh0 = (v.x - st.x) * st.y, xh1 = (v.y - st.x) * st.y;
-        float dg0 = d.x * g.x, dg1 = d.y * g.y;
-        float m1 = warp_sum(dg0 + dg1) * (1.0f / LN_C);
-        float m2 = warp_sum(dg0 * xh0 + dg1 * xh1) * (1.0f / LN_C);
-        float2 o = make_float2(st.y * (dg0 - m1 - xh0 * m2), st.y * (dg1 - m1 - xh1 * m2));
-        if (res) { float2 r = __ldg(reinterpret_cast<const float2*>(res + row * ldr) + lane); o.x += r.x; o.y += r.y; }
-        if (res2) { float2 r = __ldg(reinterpret_cast<const float2*>(res2 + row * ldr2) + lane); o.x += r.x; o.y += r.y; }
-        reinterpret_cast<float2*>(dx + row * lddx)[lane] = o;
-        if (dz) {
-            float s0 = zalpha, s1 = zalpha;
-            if (zthr) {
-                const uint32_t h = cmgan_pair_hash(zs32, (uint64_t)row * (LN_C / 2) + lane);
-                s0 = (h & 0xFFFFu) >= zt16 ? zalpha * zinv_keep : 0.f;
-                s1 = (h >> 16) >= zt16 ? zalpha * zinv_keep : 0.f;
+    const float zk = zalpha * zinv_keep;
+    for (int i = 0; i < rows_per_warp; i += 2) {
+        const long row = r0 + i;
+        const bool ok = row < M;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), d = v, r = v;
+        float2 st = make_float2(0.f, 0.f);
+        if (ok) {
+            v = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + hl);
+            d = __ldg(reinterpret_cast<const float4*>(dy + row * lddy) + hl);
+            st = __ldg(stats + row);
+            if (res) r = __ldg(reinterpret_cast<const float4*>(res + row * ldr) + hl);
+            if (res2) {
+                const float4 r2 = __ldg(reinterpret_cast<const float4*>(res2 + row * ldr2) + hl);
+                r.x += r2.x; r.y += r2.y; r.z += r2.z; r.w += r2.w;
             }
-            reinterpret_cast<float2*>(dz + row * lddz)[lane] = make_float2(cmgan_maybe_rna(o.x * s0, rnd), cmgan_maybe_rna(o.y * s1, rnd));
         }
-        ag.x += d.x * xh0; ag.y += d.y * xh1; ab.x += d.x; ab.y += d.y;
+        const float xh0 = (v.x - st.x) * st.y, xh1 = (v.y - st.x) * st.y, xh2 = (v.z - st.x) * st.y, xh3 = (v.w - st.x) * st.y;
+        const float dg0 = d.x * g.x, dg1 = d.y * g.y, dg2 = d.z * g.z, dg3 = d.w * g.w;
+        const float m1 = half_warp_sum((dg0 + dg1) + (dg2 + dg3)) * (1.0f / LN_C);
+        const float m2 = half_warp_sum((dg0 * xh0 + dg1 * xh1) + (dg2 * xh2 + dg3 * xh3)) * (1.0f / LN_C);
+        const float4 o = make_float4(st.y * (dg0 - m1 - xh0 * m2) + r.x, st.y * (dg1 - m1 - xh1 * m2) + r.y,
+                                     st.y * (dg2 - m1 - xh2 * m2) + r.z, st.y * (dg3 - m1 - xh3 * m2) + r.w);
+        if (ok) {
+            reinterpret_cast<float4*>(dx + row * lddx)[hl] = o;
+            if (dz) {
+                float s0 = zalpha, s1 = zalpha, s2 = zalpha, s3 = zalpha;
+                if (zthr) {          // one hash per pair of channels (2 p, 2 p + 1), pair index = row * 32 + p
+                    const uint32_t h0 = cmgan_pair_hash(zs32, (uint64_t)row * (LN_C / 2) + 2 * hl);
+                    const uint32_t h1 = cmgan_pair_hash(zs32, (uint64_t)row * (LN_C / 2) + 2 * hl + 1);
+                    s0 = (h0 & 0xFFFFu) >= zt16 ? zk : 0.f; s1 = (h0 >> 16) >= zt16 ? zk : 0.f;
+                    s2 = (h1 & 0xFFFFu) >= zt16 ? zk : 0.f; s3 = (h1 >> 16) >= zt16 ? zk : 0.f;
+                }
+                reinterpret_cast<float4*>(dz + row * lddz)[hl] = make_float4(cmgan_maybe_rna(o.x * s0, rnd), cmgan_maybe_rna(o.y * s1, rnd),
+                                                                             cmgan_maybe_rna(o.z * s2, rnd), cmgan_maybe_rna(o.w * s3, rnd));
+            }
+        }
+        ag.x = fmaf(d.x, xh0, ag.x); ag.y = fmaf(d.y, xh1, ag.y); ag.z = fmaf(d.z, xh2, ag.z); ag.w = fmaf(d.w, xh3, ag.w);
+        ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
     }
-    sg[warp][2 * lane] = ag.x; sg[warp][2 * lane + 1] = ag.y;
-    sb[warp][2 * lane] = ab.x; sb[warp][2 * lane + 1] = ab.y;
+    sg[warp * 2 + hw][hl] = ag;
+    sb[warp * 2 + hw][hl] = ab;
     __syncthreads();
     if (threadIdx.x < LN_C) {
         float a = 0.f, b = 0.f;
-        for (int w = 0; w < nw; ++w) { a += sg[w][threadIdx.x]; b += sb[w][threadIdx.x]; }
+        for (int w = 0; w < 2 * nw; ++w) { a += reinterpret_cast<const float*>(sg[w])[threadIdx.x]; b += reinterpret_cast<const float*>(sb[w])[threadIdx.x]; }
         atomicAdd(dgamma + threadIdx.x, a);
         atomicAdd(dbeta + threadIdx.x, b);
     }
@@ -426,9 +458,11 @@ CMGAN_API int cmgan_ln_stats(const float* x, long long ldx, long long M, float* 
 // y = LayerNorm(x) * gamma + beta + res  (res, stats optional); reference conformer.py:214,222 + generator.py:95,97
 CMGAN_API int cmgan_ln_apply(const float* x, long long ldx, long long M, const float* gamma, const float* beta,
                              const float* res, long long ldr, float* y, long long ldy, float* stats, int round_tf32, void* stream) {
-    CMGAN_REQUIRE(x && y && gamma && beta && ldx % 2 == 0 && ldy % 2 == 0 && ldr % 2 == 0, "cmgan_ln_apply: bad arguments");
+    CMGAN_REQUIRE(x && y && gamma && beta && ldx % 4 == 0 && ldy % 4 == 0 && ldr % 4 == 0 &&
+                  ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)res) | ((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) == 0,
+                  "cmgan_ln_apply: pointers must be 16-byte aligned, leading dimensions multiples of 4");
     if (M == 0) return 0;
-    ln_apply_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, M, gamma, beta, res, ldr, y, ldy,
+    ln_apply_kernel<<<cdiv(M, 8 * LN_RPW), 256, 0, (cudaStream_t)stream>>>(x, ldx, M, gamma, beta, res, ldr, y, ldy,
                                                                  reinterpret_cast<float2*>(stats), round_tf32);
     return cmgan_check_launch("ln_apply_kernel");
 }
@@ -438,7 +472,9 @@ static int ln_bwd_launch(const float* dy, long long lddy, const float* x, long l
                          float* dbeta, float* dz, long long lddz, float zalpha, unsigned long long zseed, unsigned zthr, float zinv_keep,
                          const unsigned long long* seed_dev, void* stream, const char* who) {
     CMGAN_REQUIRE(dy && x && stats && gamma && dx && dgamma && dbeta, "%s: null pointer", who);
-    CMGAN_REQUIRE(lddy % 2 == 0 && ldx % 2 == 0 && lddx % 2 == 0 && ldr % 2 == 0 && ldr2 % 2 == 0 && lddz % 2 == 0, "%s: odd leading dimension", who);
+    CMGAN_REQUIRE(lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && ldr % 4 == 0 && ldr2 % 4 == 0 && lddz % 4 == 0 &&
+                  ((((uintptr_t)dy) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)res) | ((uintptr_t)res2) | ((uintptr_t)dz) | ((uintptr_t)gamma)) & 15) == 0,
+                  "%s: pointers must be 16-byte aligned, leading dimensions multiples of 4", who);
     if (M == 0) return 0;
     const int rpw = 16;
     ln_bwd_kernel<<<cdiv(M, 8 * rpw), 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, reinterpret_cast<const float2*>(stats), gamma, M, res, ldr,

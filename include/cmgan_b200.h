@@ -27,6 +27,7 @@ int cmgan_set_tf32_rounding(int on);
 int cmgan_gemm_rows_f32(const CmganGemmArgs* a, void* stream);
 int cmgan_gemm_wgrad_f32(const CmganGemmArgs* a, void* stream);
 int cmgan_pack_weights(const CmganPackDesc* descs, int n, void* stream);
+int cmgan_pack_weight(const float* src, float* dst, long long sb_tap, long long sb_k, long long sb_n, int Cin, int ntaps, int N, void* stream);
 
 /* ---- fused macaron feed-forward (conformer.py:54-72,136-148,211-212): LN -> 64x256 -> Swish, dropout -> 256x64 -> dropout, alpha, residual in ONE tcgen05 kernel */
 int cmgan_ffn_fwd(const float* x, long long ldx, long long M, const float* ln_g, const float* ln_b, const float* W1p, const float* b1, const float* W2p, const float* b2, float alpha, unsigned long long seed1, unsigned long long seed2, unsigned int thr, float inv_keep, const unsigned long long* seed_dev, float* out, long long ldo, void* stream);
@@ -106,6 +107,17 @@ int cmgan_counter_add(unsigned long long* p, unsigned long long v, void* stream)
 int cmgan_ssnr_f64(const double* clean, const double* proc, long long L, int W, int skip, int nfr, double* out, void* stream);
 long long cmgan_stoi_scratch_doubles(long long L);
 int cmgan_stoi_f64(const double* clean, const double* proc, long long L, const double* h, const int* band_lo, const int* band_hi, double* scratch, double* out, void* stream);
+
+/* ---- module level: TSCNet.forward, inference mode (generator.py:160-196; eval BatchNorm, no dropout) as one call.
+ * params = every floating-point state_dict tensor of the reference TSCNet(64, 201) in state_dict order, each starting at a multiple of 4
+ * floats (cmgan_tscnet_param_info enumerates key / offset / numel; cmgan_tscnet_param_floats = size of the block).  x is (B, 2, T, F) with
+ * element strides (the reference passes a permuted view, train.py:95); outputs are contiguous (B, 1, T, F).  The workspace is caller-owned,
+ * 256-byte aligned, at least cmgan_tscnet_workspace_bytes(B, T, F, precision) bytes; precision 0 = exact fp32, 1 = tf32 tensor cores. */
+int cmgan_tscnet_param_count(void);
+long long cmgan_tscnet_param_floats(void);
+int cmgan_tscnet_param_info(int index, const char** key, long long* offset, long long* numel);
+long long cmgan_tscnet_workspace_bytes(int B, int T, int F, int precision);
+int cmgan_tscnet_fwd(const float* params, const float* x, long long sxb, long long sxc, long long sxt, long long sxf, int B, int T, int F, float* final_real, float* final_imag, void* workspace, long long workspace_bytes, int precision, void* stream);
 
 #ifdef __cplusplus
 }
