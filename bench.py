@@ -529,23 +529,63 @@ def extras(args, out, trainer, model, dev, step_ms):
     del probe
     step_s = step_ms * 1e-3
     achieved = b_rows / t_rows / 1e9 if t_rows > 0 else 0.0
-    traffic, traffic_note = None, "no ncu capture committed for this round yet"
+    # The row-parallel GEMM family (tcgen05 tf32): K = 64 .. 256 against N = 64 .. 256 is 13 - 64 flop/byte, far below the ~110 flop/byte
+    # balance point of tf32 tensor cores vs HBM, so the family is HBM-bound and is reported as such (algorithmic bytes of each launch).
+    out["gemm_family"] = {"bound": "hbm", "kernel": "gemm_rows_tc_kernel (every dense contraction of the generator step outside the fused FFN: linear, "
+                                                    "pointwise, dilated/strided conv)",
+                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                          "how": "sum of algorithmic bytes (A once, C, epilogue operands, weights) over every launch of one generator step / CUDA-event time "
+                                 "of those launches replayed back to back",
+                          "launches_per_step": len(rows), "share_of_step": t_rows / step_s, "algorithmic_gb_per_step": b_rows / 1e9,
+                          "tensor": {"achieved_tflops": f_rows / t_rows / 1e12 if t_rows > 0 else 0.0, "peak_tflops": tf32_peak,
+                                     "algorithmic_gflop_per_step": f_rows / 1e9},
+                          "wgrad": {"achieved": (b_wg / t_wg / 1e9) if t_wg > 0 else 0.0, "unit": "GB/s",
+                                    "frac": (b_wg / t_wg / 1e9 / hbm_peak) if t_wg > 0 else 0.0, "share_of_step": t_wg / step_s,
+                                    "achieved_tflops": (f_wg / t_wg / 1e12) if t_wg > 0 else 0.0}}
+
+    # ---- the dominant single kernel of the step (profiles/r2_launch_summary.md: 17.6 % of the kernel time, 8 launches): attention backward
+    # dq / dE (attn_bwd_dq_mma_kernel).  Timed alone here, on the bench batch's shapes, both sequence axes (4 launches each per step).
+    # Algorithmic flops (SURVEY 8d counts attention as L^2 d MACs per contraction, rel-pos term included): this kernel owns three of the six
+    # backward contractions -- dQ = dS K, dQ += dR E, dE = dR^T Q -- = 3 x 2 x 16 = 96 flop per (query, key) pair and head.  It also recomputes
+    # S, R and dP (not counted).  Bound: tensor pipe (compulsory traffic ~0.9 GB per launch = 0.14 ms at HBM speed vs 0.09 ms of tf32 math).
+    H_, D_ = 4, 16
+    Ew = torch.randn(1025, D_, device=dev) * 0.1
+    dq_us, dq_flop = [], []
+    for axis, L, nseq in ((0, T, B * F2), (1, F2, B * T)):
+        qkv = torch.randn(M, 3 * 64, device=dev) * 0.5
+        dctx = torch.randn(M, 64, device=dev) * 0.1
+        ctx, lse = torch.empty(M, 64, device=dev), torch.empty(M, H_, device=dev)
+        delta, dqkv, dE = torch.empty(M, H_, device=dev), torch.empty(M, 3 * 64, device=dev), torch.zeros(1025, D_, device=dev)
+        ops.call("cmgan_attention_fwd_tf32", qkv, Ew, B, T, F2, axis, ctx, lse)
+        ops.call("cmgan_attention_bwd_tf32_parts", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 1)       # delta only
+        for _ in range(2):
+            ops.call("cmgan_attention_bwd_tf32_parts", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 2)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(4):
+            ops.call("cmgan_attention_bwd_tf32_parts", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 2)   # dq + dE kernel only
+        a1.record()
+        torch.cuda.synchronize()
+        dq_us.append(a0.elapsed_time(a1) / 4 * 1e3)
+        dq_flop.append(96.0 * nseq * H_ * L * L)
+        del qkv, dctx, ctx, lse, delta, dqkv, dE
+    dq_t = sum(dq_us) / len(dq_us) * 1e-6                    # average launch duration over the step's 4 + 4 launches
+    dq_f = sum(dq_flop) / len(dq_flop)
+    traffic, traffic_note = None, "no ncu capture committed for this batch size"
     tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    if os.path.exists(tp):           # dram read + write per launch of the dominant kernel, parsed from a committed ncu --set full report
+    if os.path.exists(tp):           # dram read + write per launch of the same kernel at the same batch, from the committed ncu launch list
         tj = json.load(open(tp))
-        traffic, traffic_note = tj.get("traffic_bytes_per_launch"), tj.get("note", "")
-    # The dominant kernel family is the row-parallel GEMM (tcgen05 tf32): K = 64 .. 256 against N = 64 .. 256 is 13 - 64 flop/byte,
-    # far below the ~110 flop/byte balance point of tf32 tensor cores vs HBM, so the family is HBM-bound and is reported as such.
-    out["roofline"] = {"bound": "hbm", "kernel": "gemm_rows_tc_kernel (every dense contraction of the generator step: linear, pointwise, dilated/strided conv)",
-                       "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                       "peak_source": f"{psrc}: hbm_gbs (copy bandwidth, read + write)",
-                       "how": "sum of algorithmic bytes (A once, C, epilogue operands, weights) over every launch of one generator step / CUDA-event time of "
-                              "those launches replayed back to back",
-                       "launches_per_step": len(rows), "share_of_step": t_rows / step_s, "algorithmic_gb_per_step": b_rows / 1e9,
-                       "tensor": {"achieved_tflops": f_rows / t_rows / 1e12 if t_rows > 0 else 0.0, "peak_tflops": tf32_peak,
-                                  "algorithmic_gflop_per_step": f_rows / 1e9},
-                       "wgrad": {"achieved": (b_wg / t_wg / 1e9) if t_wg > 0 else 0.0, "unit": "GB/s", "frac": (b_wg / t_wg / 1e9 / hbm_peak) if t_wg > 0 else 0.0,
-                                 "share_of_step": t_wg / step_s, "achieved_tflops": (f_wg / t_wg / 1e12) if t_wg > 0 else 0.0},
+        if tj.get("batch") == B:
+            traffic, traffic_note = tj.get("traffic_bytes_per_launch"), tj.get("note", "")
+    tf32_burst = peaks.get("bf16_tflops", 1590.0) / 2.0        # kernel timed alone: the burst figure
+    out["roofline"] = {"bound": "tensor", "kernel": "attn_bwd_dq_mma_kernel (attention backward: dQ, dE; mma.sync tf32)", "achieved": dq_f / dq_t / 1e12,
+                       "peak": tf32_burst, "unit": "TFLOP/s", "frac": dq_f / dq_t / 1e12 / tf32_burst,
+                       "peak_source": f"{psrc}: bf16_tflops (burst, kernel timed alone) / 2 (tf32 runs at half the bf16 rate)",
+                       "how": "96 algorithmic flop per (query, key) pair and head x pairs of one launch / CUDA-event duration of that launch, averaged over "
+                              "the time-axis and frequency-axis shapes of the bench batch (4 launches each per step); the kernel timed alone, 4 repeats",
+                       "launch_us": {"time_axis": dq_us[0], "freq_axis": dq_us[1]}, "launches_per_step": 8,
+                       "share_of_step": 4 * (dq_us[0] + dq_us[1]) * 1e-6 / step_s, "algorithmic_gflop_per_launch": dq_f / 1e9,
                        "traffic": traffic, "traffic_note": traffic_note}
 
     # ---- the same-box competitor (SURVEY 8d / BASELINE.md 4.5): the reference's modules in PyTorch eager on this B200, generator forward +

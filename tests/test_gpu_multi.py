@@ -74,3 +74,53 @@ def test_two_rank_gradients_equal_single_gpu_batch(tmp_path):
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         print(f"[dp2] {key}: 2 x B=2 (all-reduce AVG) vs 1 x B=4: max-abs deviation / max {err:.3e}")
         assert np.isfinite(err) and err < tol, key
+
+
+def _ddp_worker(rank, world, port, gpath, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    import cmgan_b200
+    from cmgan_b200 import training
+    from oracle import cmgan_oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        g = torch.Generator().manual_seed(rank)
+        clean = (0.05 * torch.randn(2, 8000, generator=g)).to(dev)
+        noisy = clean + (0.05 * torch.randn(2, 8000, generator=g)).to(dev)
+        grads = []
+        for wrap in (False, True):
+            m = cmgan_b200.TSCNet(64, 201)
+            m.load_state_dict(O.load_weights_npz(gpath), strict=True)
+            m = m.to(dev).eval()                                      # eval: no dropout, so both passes see the same function
+            model = DDP(m, device_ids=[rank]) if wrap else m          # train.py:68: DDP(self.model, device_ids=[gpu_id])
+            outp = training.forward_generator_step(model, clean, noisy)
+            loss = training.generator_loss(outp, clean)
+            loss.backward()
+            torch.cuda.synchronize()
+            grads.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu())
+            assert set(model.state_dict().keys()) == {("module." + k if wrap else k) for k in m.state_dict().keys()}     # train.py:273 saves model.module
+        if rank == 0:
+            torch.save(dict(plain=grads[0], ddp=grads[1]), out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a GPU")
+def test_module_inside_ddp(tmp_path):
+    """the reference wraps TSCNet in DistributedDataParallel (train.py:68-69): parameters must be leaf tensors DDP can hook, the forward must
+    run through the wrapper, and with one rank the averaged gradients equal the unwrapped module's"""
+    import torch.multiprocessing as mp
+    gpath = os.path.join(ROOT, "tests", "golden", "weights_g.npz")
+    out = str(tmp_path / "ddp.pt")
+    mp.spawn(_ddp_worker, args=(1, _free_port(), gpath, out), nprocs=1, join=True)
+    r = torch.load(out)
+    ref, got = r["plain"].double(), r["ddp"].double()
+    assert ref.abs().max().item() > 0
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    print(f"[ddp] DDP-wrapped vs plain module gradients: {err:.3e}")
+    assert err < 1e-5
