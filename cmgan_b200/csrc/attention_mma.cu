@@ -292,38 +292,51 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
     if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0, 0);
     cp_async_commit();
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // ---- per-item row operands: q (scaled), dO as A fragments; delta, lse for rows gq, gq + 8.  They are fetched one item ahead -- the
+    // loads are issued while the previous item's last key tile is being processed -- so an item does not start by waiting for global memory
+    // (that wait was 22 % of the kernel's stall samples: a sequence has only 2 - 6 key tiles to amortise it over).
+    float qn[2][4], dn[2][4], dln[2], lsn[2];
+    auto fetch_item = [&](int item) {
         const int s = item / H, h = item % H;
         const long base = seq_base(g, s);
-        // ---- per-item row operands: q (scaled), dO as A fragments; delta, lse for rows gq, gq+8
-        float qa[2][4], da[2][4], dl[2] = {0.f, 0.f}, ls[2] = {0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int row = iw + gq + (r & 1) * 8, col = t + (r >> 1) * 4 + ks * 8;
-                float qv = 0.f, dv = 0.f, ov = 0.f;
+                float qv = 0.f, dv = 0.f;
                 if (row < g.L) {
                     const long rr = base + (long)row * g.tok_stride;
-                    qv = __ldg(qkv + rr * LDQ + h * D + col) * SCALE_LOG2E;
+                    qv = __ldg(qkv + rr * LDQ + h * D + col);
                     dv = __ldg(dctx + rr * CQ + h * D + col);
-                    ov = __ldg(ctx + rr * CQ + h * D + col);
                 }
-                qa[ks][r] = tf32r(qv);
-                da[ks][r] = tf32r(dv);
-                dl[r & 1] = fmaf(dv, ov, dl[r & 1]);
+                qn[ks][r] = qv;
+                dn[ks][r] = dv;
             }
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
-            dl[hrow] += __shfl_xor_sync(0xffffffffu, dl[hrow], 1);
-            dl[hrow] += __shfl_xor_sync(0xffffffffu, dl[hrow], 2);
             const int row = iw + gq + hrow * 8;
+            lsn[hrow] = 0.f; dln[hrow] = 0.f;
             if (row < g.L) {
                 const long rr = base + (long)row * g.tok_stride;
-                ls[hrow] = __ldg(lse + rr * H + h);
-                dl[hrow] = __ldg(delta + rr * H + h);          // written by attn_delta_kernel (the dk / dv kernel reads the same values)
+                lsn[hrow] = __ldg(lse + rr * H + h);
+                dln[hrow] = __ldg(delta + rr * H + h);          // written by attn_delta_kernel (the dk / dv kernel reads the same values)
             }
         }
+    };
+    if ((int)blockIdx.x < n_items) fetch_item(blockIdx.x);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int s = item / H, h = item % H;
+        const long base = seq_base(g, s);
+        float qa[2][4], da[2][4], dl[2], ls[2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                qa[ks][r] = tf32r(qn[ks][r] * SCALE_LOG2E);
+                da[ks][r] = tf32r(dn[ks][r]);
+            }
+        dl[0] = dln[0]; dl[1] = dln[1]; ls[0] = lsn[0]; ls[1] = lsn[1];
         float dq[2][4];
 #pragma unroll
         for (int nd = 0; nd < 2; ++nd)
@@ -340,7 +353,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
                     for (int r = 0; r < 4; ++r) Qw[(gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8] = qa[ks][r];
             }
             if (j0 + KT < g.L) stage(item, j0 + KT, (it + 1) & 1);
-            else if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, 0, (it + 1) & 1);
+            else if (item + (int)gridDim.x < n_items) {
+                stage(item + gridDim.x, 0, (it + 1) & 1);
+                fetch_item(item + gridDim.x);          // consumed when the next item starts
+            }
             cp_async_commit();
             cp_async_wait<1>();
             __syncthreads();
