@@ -39,6 +39,9 @@ def main():
         def fwd(i):
             call("cmgan_attention_fwd_tf32", qkvs[i % nb], E, B, T, F2, axis, ctx, lse)
 
+        def fwd1(i):
+            call("cmgan_attention_fwd_tf32_nbuf", qkvs[i % nb], E, B, T, F2, axis, ctx, lse, 1)
+
         def fwd_tc(i):
             call("cmgan_attention_fwd_tc", qkvs[i % nb], E, B, T, F2, axis, ctx, lse)
 
@@ -52,7 +55,12 @@ def main():
             ops.call_on(side, "cmgan_attention_bwd_tf32_parts", *args, 4)
             call("cmgan_attention_bwd_tf32_parts", *args, 2)
             ops.join(side)
-        for fn, key in ((fwd, "fwd"), (fwd_tc, "fwd_tc"), (bwd, "bwd"), (bwd2, "bwd_two_streams")):
+        ctx2, lse2 = torch.empty_like(ctx), torch.empty_like(lse)
+        call("cmgan_attention_fwd_tf32_nbuf", qkvs[0], E, B, T, F2, axis, ctx, lse, 2)
+        call("cmgan_attention_fwd_tf32_nbuf", qkvs[0], E, B, T, F2, axis, ctx2, lse2, 1)
+        torch.cuda.synchronize()
+        assert torch.equal(ctx, ctx2) and torch.equal(lse, lse2), "single- and double-buffered forward disagree"
+        for fn, key in ((fwd, "fwd"), (fwd1, "fwd_single_buffer"), (fwd_tc, "fwd_tc"), (bwd, "bwd"), (bwd2, "bwd_two_streams")):
             for i in range(3):
                 fn(i)
             torch.cuda.synchronize()
