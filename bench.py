@@ -558,13 +558,15 @@ def extras(args, out, trainer, model, dev, step_ms):
         delta, dqkv, dE = torch.empty(M, H_, device=dev), torch.empty(M, 3 * 64, device=dev), torch.zeros(1025, D_, device=dev)
         ops.call("cmgan_attention_fwd_tf32", qkv, Ew, B, T, F2, axis, ctx, lse)
         ops.call("cmgan_attention_bwd_tf32_parts", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 1)       # delta only
+        nws = _lib().cdll.cmgan_attention_bwd_ws_floats(B, T, F2, axis) if ops.ATTN_BWD_WS else 0
+        wsb = torch.empty(max(nws, 1), device=dev) if nws else None
         for _ in range(2):
-            ops.call("cmgan_attention_bwd_tf32_parts", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 2)
+            ops.call("cmgan_attention_bwd_tf32_ws", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 2, wsb, nws)
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(4):
-            ops.call("cmgan_attention_bwd_tf32_parts", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 2)   # dq + dE kernel only
+            ops.call("cmgan_attention_bwd_tf32_ws", qkv, Ew, ctx, dctx, lse, B, T, F2, axis, delta, dqkv, dE, 2, wsb, nws)   # dq + dE kernel only, as the step runs it
         a1.record()
         torch.cuda.synchronize()
         dq_us.append(a0.elapsed_time(a1) / 4 * 1e3)

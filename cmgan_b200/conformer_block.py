@@ -15,6 +15,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
+from ._lib import lib
 from .ops import EPI_ACC, EPI_DBNSWISH, EPI_DROP_RES, EPI_DSWISH_DROP, EPI_SWISH_DUAL, call, gemm
 
 C = 64          # num_channel (the kernels are specialised for 64 channels = 4 heads x 16)
@@ -257,14 +258,21 @@ def conformer_bwd(dy, S: dict, P, G: Dict[str, torch.Tensor], B, T, F2, sums: _S
     dqkv = _empty(M, 3 * C, dev=dev)
     delta = _empty(M, 4, dev=dev)
     attn_args = (S["qkv"], P[f"{p}.attn.fn.rel_pos_emb.weight"], S["ctx"], dctx, S["lse"], B, T, F2, axis, delta, dqkv, G[f"{p}.attn.fn.rel_pos_emb.weight"])
-    if ops.PRECISION == 1 and ops.AUX_STREAM is not None and ops.PROBE is None:
-        # delta first; then the dq / dE kernel and the dk / dv kernel side by side (each alone leaves most of every SM idle)
-        call("cmgan_attention_bwd_tf32_parts", *attn_args, 1)
-        ops.call_on(ops.AUX_STREAM, "cmgan_attention_bwd_tf32_parts", *attn_args, 4)
-        call("cmgan_attention_bwd_tf32_parts", *attn_args, 2)
-        ops.join(ops.AUX_STREAM)
+    if ops.PRECISION == 1:
+        ws, nws = None, 0
+        if ops.ATTN_BWD_WS:         # block-private dE accumulators in global memory: the dq kernel runs 3 blocks / SM instead of 2
+            nws = lib().cdll.cmgan_attention_bwd_ws_floats(B, T, F2, axis)
+            ws = _empty(max(nws, 1), dev=dev)
+        if ops.AUX_STREAM is not None and ops.PROBE is None:
+            # delta first; then the dq / dE kernel and the dk / dv kernel side by side (each alone leaves most of every SM idle)
+            call("cmgan_attention_bwd_tf32_ws", *attn_args, 1, None, 0)
+            ops.call_on(ops.AUX_STREAM, "cmgan_attention_bwd_tf32_ws", *attn_args, 4, None, 0)
+            call("cmgan_attention_bwd_tf32_ws", *attn_args, 2, ws, nws)
+            ops.join(ops.AUX_STREAM)
+        else:
+            call("cmgan_attention_bwd_tf32_ws", *attn_args, 7, ws, nws)
     else:
-        call("cmgan_attention_bwd_tf32" if ops.PRECISION == 1 else "cmgan_attention_bwd", *attn_args)
+        call("cmgan_attention_bwd", *attn_args)
     dln2 = _empty(M, C, dev=dev)
     Wq, Wkv = P[f"{p}.attn.fn.to_q.weight"], P[f"{p}.attn.fn.to_kv.weight"]
     Gq, Gkv = G[f"{p}.attn.fn.to_q.weight"], G[f"{p}.attn.fn.to_kv.weight"]

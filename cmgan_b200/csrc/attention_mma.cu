@@ -275,15 +275,20 @@ __global__ void attn_delta_kernel(const float* __restrict__ ctx, const float* __
 //                                           block accumulator (no atomics: shared fp32 atomics are CAS loops)
 // dynamic smem: (Ks | Vs | Es)[2] | Rb[64 x LDRB] | Qs[64 x 20] | dEs[(Lpad + 64) x 16]
 constexpr int LDRB = 136;
-__global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
+// GDE = false: the dE accumulator lives in shared memory next to two tile buffers (110 KB at L = 321: 2 blocks / SM, 1 at L = 1281).
+// GDE = true : the accumulator is a block-private slab of global memory (L2-resident read-modify-write, no atomics: a block owns its slab) and
+//              the K / V / E tile is single-buffered: 60 KB -> 3 blocks / SM at every L; the other resident blocks hide the tile loads.
+template <bool GDE>
+__global__ void __launch_bounds__(128, GDE ? 3 : 2) attn_bwd_dq_mma_kernel(const float* __restrict__ qkv, SeqGeom g, const float* __restrict__ E,
                                                               const float* __restrict__ ctx, const float* __restrict__ dctx,
                                                               const float* __restrict__ lse, int n_items, int Lpad,
                                                               float* __restrict__ delta, float* __restrict__ dqkv,
-                                                              float* __restrict__ dE) {
+                                                              float* __restrict__ dE, float* __restrict__ de_scratch) {
     extern __shared__ __align__(16) float smem_dq[];
-    float* Rb = smem_dq + 2 * TILE_FLOATS;            // after the two K / V / E tile buffers
+    constexpr int NBUF = GDE ? 1 : 2;
+    float* Rb = smem_dq + NBUF * TILE_FLOATS;         // after the K / V / E tile buffer(s)
     float* Qs = Rb + QB * LDRB;
-    float* dEs = Qs + QB * LDS_;
+    float* dEs = GDE ? de_scratch + ((long)blockIdx.y * gridDim.x + blockIdx.x) * (long)(Lpad + 64) * D : Qs + QB * LDS_;
     const int i0 = blockIdx.y * QB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
     const int iw = i0 + warp * 16;
@@ -301,8 +306,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
         stage_tile_async(smem_dq + slot * TILE_FLOATS, qkv + h * D + CQ, LDQ, qkv + h * D + 2 * CQ, LDQ, seq_base(g, s), g.tok_stride, j0, g.L, E,
                          i0 - j0 - (KT - 1), tid);
     };
-    if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0, 0);
-    cp_async_commit();
+    if (!GDE) {
+        if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0, 0);
+        cp_async_commit();
+    }
     int it = 0;
     // ---- per-item row operands: q (scaled), dO as A fragments; delta, lse for rows gq, gq + 8.  They are fetched one item ahead -- the
     // loads are issued while the previous item's last key tile is being processed -- so an item does not start by waiting for global memory
@@ -336,10 +343,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
             }
         }
     };
-    if ((int)blockIdx.x < n_items) fetch_item(blockIdx.x);
+    if (!GDE && (int)blockIdx.x < n_items) fetch_item(blockIdx.x);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int s = item / H, h = item % H;
         const long base = seq_base(g, s);
+        if (GDE) fetch_item(item);         // three resident blocks hide this latency; the prefetch registers would cost the third block
         float qa[2][4], da[2][4], dl[2], ls[2];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
@@ -364,15 +372,21 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __res
 #pragma unroll
                     for (int r = 0; r < 4; ++r) Qw[(gq + (r & 1) * 8) * LDS_ + t + (r >> 1) * 4 + ks * 8] = qa[ks][r];
             }
-            if (j0 + KT < g.L) stage(item, j0 + KT, (it + 1) & 1);
-            else if (item + (int)gridDim.x < n_items) {
-                stage(item + gridDim.x, 0, (it + 1) & 1);
-                fetch_item(item + gridDim.x);          // consumed when the next item starts
+            if (GDE) {
+                stage(item, j0, 0);
+                cp_async_commit();
+                cp_async_wait<0>();
+            } else {
+                if (j0 + KT < g.L) stage(item, j0 + KT, (it + 1) & 1);
+                else if (item + (int)gridDim.x < n_items) {
+                    stage(item + gridDim.x, 0, (it + 1) & 1);
+                    fetch_item(item + gridDim.x);          // consumed when the next item starts
+                }
+                cp_async_commit();
+                cp_async_wait<1>();
             }
-            cp_async_commit();
-            cp_async_wait<1>();
             __syncthreads();
-            const float* Ks = smem_dq + (it & 1) * TILE_FLOATS;
+            const float* Ks = smem_dq + (GDE ? 0 : (it & 1)) * TILE_FLOATS;
             const float* Vs = Ks + KT * LDS_;
             const float* Es = Vs + KT * LDS_;
             ++it;
@@ -701,40 +715,67 @@ CMGAN_API int cmgan_attention_fwd_tf32_nbuf(const float* qkv, const float* E, in
 // parts: bit 0 = delta, bit 1 = dq + dE (reads delta), bit 2 = dk / dv (reads delta).  The two big kernels are independent of each other once
 // delta exists and each one alone leaves most of an SM idle (8 - 12 resident warps, barrier- and latency-bound), so the caller may run
 // part 1 first and then parts 2 and 4 on two streams; cmgan_attention_bwd_tf32 = all parts in order on one stream.
-CMGAN_API int cmgan_attention_bwd_tf32_parts(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
-                                             int T, int F, int axis, float* delta, float* dqkv, float* dE, int parts, void* stream) {
+// scratch (optional, cmgan_attention_bwd_ws_floats): block-private dE accumulators in global memory -> the dq kernel needs 60 KB instead of
+// 110+ KB of shared memory and runs 3 blocks / SM (any L) instead of 2 (1 at L = 1281).
+static int dq_blocks(int ntile, int per_sm, int n_items) {
+    int ng = (148 * per_sm) / ntile;
+    if (ng < 1) ng = 1;
+    return ng > n_items ? n_items : ng;
+}
+
+CMGAN_API long long cmgan_attention_bwd_ws_floats(int B, int T, int F, int axis) {
+    if (axis != 0 && axis != 1) { cmgan_set_error("cmgan_attention_bwd_ws_floats: axis must be 0 (time) or 1 (freq)"); return -1; }
+    SeqGeom g = make_seq_geom(B, T, F, axis);
+    if (g.n_seq == 0 || g.L == 0) return 0;
+    const int ntile = cdiv(g.L, QB), Lpad = ntile * KT;
+    return (long long)dq_blocks(ntile, 3, g.n_seq * H) * ntile * (Lpad + 64) * D;
+}
+
+CMGAN_API int cmgan_attention_bwd_tf32_ws(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
+                                          int T, int F, int axis, float* delta, float* dqkv, float* dE, int parts, float* scratch,
+                                          long long scratch_floats, void* stream) {
     CMGAN_REQUIRE(qkv && E && ctx && dctx && lse && delta && dqkv && dE, "cmgan_attention_bwd_tf32: null pointer");
     CMGAN_REQUIRE(axis == 0 || axis == 1, "cmgan_attention_bwd_tf32: axis must be 0 (time) or 1 (freq)");
     SeqGeom g = make_seq_geom(B, T, F, axis);
     if (g.n_seq == 0 || g.L == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int ntile = cdiv(g.L, QB), Lpad = ntile * KT;
-    const int smem_dq = (2 * TILE_FLOATS + QB * LDRB + QB * LDS_ + (Lpad + 64) * D) * (int)sizeof(float);
+    const int n_items = g.n_seq * H;
+    const bool gde = scratch != nullptr;
+    if (gde) CMGAN_REQUIRE(scratch_floats >= cmgan_attention_bwd_ws_floats(B, T, F, axis) && (((uintptr_t)scratch) & 7) == 0,
+                           "cmgan_attention_bwd_tf32_ws: scratch too small (%lld floats) or misaligned", scratch_floats);
+    const int smem_dq = ((gde ? 1 : 2) * TILE_FLOATS + QB * LDRB + QB * LDS_ + (gde ? 0 : (Lpad + 64) * D)) * (int)sizeof(float);
     const int smem_kv = (2 * TILE_FLOATS + QB * LDR2 + 4 * QB) * (int)sizeof(float);
     CMGAN_REQUIRE(smem_dq <= 227 * 1024, "cmgan_attention_bwd_tf32: sequence length %d too long for the shared dE accumulator", g.L);
     static int smem_dq_set = 0;
-    static bool kv_set = false;
-    if (smem_dq > smem_dq_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
+    static bool kv_set = false, gde_set = false;
+    if (!gde && smem_dq > smem_dq_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
         CMGAN_REQUIRE(e == cudaSuccess, "cmgan_attention_bwd_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         smem_dq_set = smem_dq;
+    }
+    if (gde && !gde_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
+        CMGAN_REQUIRE(e == cudaSuccess, "cmgan_attention_bwd_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        gde_set = true;
     }
     if (!kv_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
         CMGAN_REQUIRE(e == cudaSuccess, "cmgan_attention_bwd_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         kv_set = true;
     }
-    const int n_items = g.n_seq * H;
-    int ng = (148 * 2) / ntile;                      // one wave of 2 resident blocks per SM
-    if (ng < 1) ng = 1;
-    if (ng > n_items) ng = n_items;
     if (parts & 1) {
         const long n = (long)B * T * F * H;
         attn_delta_kernel<<<cdiv(n, 256), 256, 0, st>>>(ctx, dctx, n, delta);
         if (cmgan_check_launch("attn_delta_kernel")) return -1;
     }
     if (parts & 2) {
-        attn_bwd_dq_mma_kernel<<<dim3(ng, ntile), 128, smem_dq, st>>>(qkv, g, E, ctx, dctx, lse, n_items, Lpad, delta, dqkv, dE);
+        if (gde)
+            attn_bwd_dq_mma_kernel<true><<<dim3(dq_blocks(ntile, 3, n_items), ntile), 128, smem_dq, st>>>(qkv, g, E, ctx, dctx, lse, n_items, Lpad,
+                                                                                                          delta, dqkv, dE, scratch);
+        else
+            attn_bwd_dq_mma_kernel<false><<<dim3(dq_blocks(ntile, 2, n_items), ntile), 128, smem_dq, st>>>(qkv, g, E, ctx, dctx, lse, n_items, Lpad,
+                                                                                                           delta, dqkv, dE, nullptr);
         if (cmgan_check_launch("attn_bwd_dq_mma_kernel")) return -1;
     }
     if (parts & 4) {
@@ -742,6 +783,11 @@ CMGAN_API int cmgan_attention_bwd_tf32_parts(const float* qkv, const float* E, c
         if (cmgan_check_launch("attn_bwd_dkv_mma_kernel")) return -1;
     }
     return 0;
+}
+
+CMGAN_API int cmgan_attention_bwd_tf32_parts(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,
+                                             int T, int F, int axis, float* delta, float* dqkv, float* dE, int parts, void* stream) {
+    return cmgan_attention_bwd_tf32_ws(qkv, E, ctx, dctx, lse, B, T, F, axis, delta, dqkv, dE, parts, nullptr, 0, stream);
 }
 
 CMGAN_API int cmgan_attention_bwd_tf32(const float* qkv, const float* E, const float* ctx, const float* dctx, const float* lse, int B,

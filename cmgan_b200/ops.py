@@ -25,6 +25,10 @@ _WGRAD_KEEP = []      # operands of in-flight side-stream launches (kept allocat
 # parity-green but 18 % slower than the mma.sync kernel (377 vs 318 us, B = 4 time axis; profiles/README.md), its softmax warps wait on a
 # serial S/R -> softmax -> PV chain with one TMEM slot per CTA.
 ATTN_TC = os.environ.get("CMGAN_ATTN_TC", "0") != "0"
+# attention backward: dE accumulators of the dq kernel in a block-private global scratch (60 KB of shared memory, 3 blocks / SM, any L) instead
+# of shared memory (110 KB at L = 321: 2 blocks / SM).  Off by default: measured equal at L = 321 (775 vs 773 us) and 5 % slower at L = 101
+# (300 vs 314 us) -- the kernel is not occupancy-bound; it is the variant to use when L > ~900, where the shared accumulator leaves 1 block / SM.
+ATTN_BWD_WS = os.environ.get("CMGAN_ATTN_BWD_WS", "0") != "0"
 FUSED_FFN = os.environ.get("CMGAN_FUSED_FFN", "1") != "0"   # tf32 mode: one tcgen05 kernel per feed-forward module (csrc/ffn_fused.cu)
 PACK_CACHE = None   # optional PackCache: re-tiled tensor-core weight operands kept across calls (owner refreshes them after every weight update)
 PROBE = None     # list collecting (entry point, M, N, K, start event, end event) when bench.py instruments a step

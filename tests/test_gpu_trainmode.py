@@ -266,6 +266,15 @@ def test_tc_attention_fwd_bwd_vs_float64(B, T, F2, axis, fwd):
     e_c, e_q, e_e = _rel(ctx, ref), _rel(dqkv, q64.grad), _rel(dE, E64.grad)
     print(f"[tf32-vs-f64] attention ({fwd[16:]} forward) B={B} T={T} F'={F2} axis={axis}: ctx {e_c:.3e}  dqkv {e_q:.3e}  dE {e_e:.3e}")
     assert e_c <= 3e-3 and e_q <= 5e-3 and e_e <= 5e-3
+    # same backward with the dE accumulators in a global scratch (3 blocks / SM variant of the dq kernel)
+    from cmgan_b200._lib import lib
+    nws = lib().cdll.cmgan_attention_bwd_ws_floats(B, T, F2, axis)
+    ws = torch.empty(nws, device=DEV)
+    dqkv2, dE2 = torch.empty(M, 192, device=DEV), torch.zeros(1025, 16, device=DEV)
+    call("cmgan_attention_bwd_tf32_ws", qkv, E, ctx, dctx, lse, B, T, F2, axis, delta, dqkv2, dE2, 7, ws, nws)
+    e_q2, e_e2 = _rel(dqkv2, q64.grad), _rel(dE2, E64.grad)
+    print(f"[tf32-vs-f64] attention backward, global dE scratch: dqkv {e_q2:.3e}  dE {e_e2:.3e}")
+    assert e_q2 <= 5e-3 and e_e2 <= 5e-3
 
 
 # ------------------------------------------------------------------------------------------------ fused feed-forward kernel

@@ -47,6 +47,18 @@ def main():
 
         def bwd(i):
             call("cmgan_attention_bwd_tf32", qkvs[i % nb], E, ctx, dctxs[i % nb], lse, B, T, F2, axis, delta, dqkv, dE)
+        from cmgan_b200._lib import lib as _lib
+        nws = _lib().cdll.cmgan_attention_bwd_ws_floats(B, T, F2, axis)
+        ws = torch.empty(nws, device=dev)
+
+        def bwd_ws(i):
+            call("cmgan_attention_bwd_tf32_ws", qkvs[i % nb], E, ctx, dctxs[i % nb], lse, B, T, F2, axis, delta, dqkv, dE, 7, ws, nws)
+
+        def dq_only(i):
+            call("cmgan_attention_bwd_tf32_ws", qkvs[i % nb], E, ctx, dctxs[i % nb], lse, B, T, F2, axis, delta, dqkv, dE, 2, None, 0)
+
+        def dq_only_ws(i):
+            call("cmgan_attention_bwd_tf32_ws", qkvs[i % nb], E, ctx, dctxs[i % nb], lse, B, T, F2, axis, delta, dqkv, dE, 2, ws, nws)
         side = torch.cuda.Stream()
 
         def bwd2(i):
@@ -60,7 +72,8 @@ def main():
         call("cmgan_attention_fwd_tf32_nbuf", qkvs[0], E, B, T, F2, axis, ctx2, lse2, 1)
         torch.cuda.synchronize()
         assert torch.equal(ctx, ctx2) and torch.equal(lse, lse2), "single- and double-buffered forward disagree"
-        for fn, key in ((fwd, "fwd"), (fwd1, "fwd_single_buffer"), (fwd_tc, "fwd_tc"), (bwd, "bwd"), (bwd2, "bwd_two_streams")):
+        for fn, key in ((fwd, "fwd"), (fwd1, "fwd_single_buffer"), (fwd_tc, "fwd_tc"), (bwd, "bwd"), (bwd_ws, "bwd_global_dE"), (dq_only, "dq"), (dq_only_ws, "dq_global_dE"),
+                        (bwd2, "bwd_two_streams")):
             for i in range(3):
                 fn(i)
             torch.cuda.synchronize()
