@@ -3,6 +3,8 @@
 // Everything is float64 like the numpy reference (tiny work: what matters is that 824 test files can be scored without leaving the GPU);
 // intermediate sizes that depend on the data (number of non-silent frames) stay on the device -- every kernel is launched over the
 // worst case and exits early -- so the entry points never synchronise.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/cmgan_b200.h"
 
@@ -199,6 +201,168 @@ __global__ void stoi_segment_kernel(const double* __restrict__ X, const double* 
     }
 }
 
+// ---- log-likelihood ratio (compute_metrics.py:277-347: llr + lpcoeff): one block per frame.  Windowed frames in shared memory, the 17
+// autocorrelation lags of both signals by one warp each (strided + shuffle reduction), Levinson-Durbin (order P <= 16) by one thread per
+// signal in shared memory and the two quadratic forms a R_c a^T by thread 0 (a few hundred flops).  out[f] = log(a_p R_c a_p^T / a_c R_c a_c^T).
+constexpr int LLR_MAXW = 512, LLR_P = 16;
+__global__ void llr_kernel(const double* __restrict__ c, const double* __restrict__ p, int W, int skip, int P, double* __restrict__ out, int serial) {
+    __shared__ double fc[LLR_MAXW], fp[LLR_MAXW], Rc[LLR_P + 1], Rp[LLR_P + 1];
+    const int f = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const long s0 = (long)f * skip;
+    const double PI = 3.14159265358979323846;
+    for (int i = tid; i < W; i += blockDim.x) {
+        const double w = 0.5 * (1.0 - cos(2.0 * PI * (double)(i + 1) / (double)(W + 1)));
+        fc[i] = c[s0 + i] * w;
+        fp[i] = p[s0 + i] * w;
+    }
+    __syncthreads();
+    if (serial) {                      // one thread per lag (diagnostic / fallback variant: no warp-level reduction)
+        if (tid < 2 * (P + 1)) {
+            const int k = tid % (P + 1);
+            const double* x = tid <= P ? fc : fp;
+            double acc = 0.0;
+            for (int i = 0; i < W - k; ++i) acc += x[i] * x[i + k];
+            if (tid <= P) Rc[k] = acc; else Rp[k] = acc;
+        }
+    } else {
+        for (int job = warp; job < 2 * (P + 1); job += nw) {
+            const int k = job % (P + 1);
+            const double* x = job <= P ? fc : fp;
+            double acc = 0.0;
+            for (int i = lane; i < W - k; i += 32) acc += x[i] * x[i + k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) { if (job <= P) Rc[k] = acc; else Rp[k] = acc; }
+        }
+    }
+    __syncthreads();
+    // Levinson-Durbin in shared memory, one thread per signal (thread 0: clean, thread 1: processed), ping-pong coefficient arrays:
+    //   k_i = (R[i+1] - sum_{j<i} a_j R[i-j]) / E_i;   a'_j = a_j - k_i a_{i-1-j} (j < i), a'_i = k_i;   E_{i+1} = (1 - k_i^2) E_i
+    __shared__ double lev[2][2][LLR_P + 1], poly[2][LLR_P + 1];
+    if (tid < 2) {
+        const double* R = tid == 0 ? Rc : Rp;
+        int cur = 0;
+        double err = R[0];
+        for (int i = 0; i < P; ++i) {
+            double acc = 0.0;
+            for (int j = 0; j < i; ++j) acc += lev[tid][cur][j] * R[i - j];
+            const double k = (R[i + 1] - acc) / err;
+            for (int j = 0; j < i; ++j) lev[tid][cur ^ 1][j] = lev[tid][cur][j] - lev[tid][cur][i - 1 - j] * k;
+            lev[tid][cur ^ 1][i] = k;
+            err = (1.0 - k * k) * err;
+            cur ^= 1;
+        }
+        poly[tid][0] = 1.0;
+        for (int i = 0; i < P; ++i) poly[tid][i + 1] = -lev[tid][cur][i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i <= P; ++i)
+            for (int j = 0; j <= P; ++j) {
+                const double r = Rc[i > j ? i - j : j - i];
+                num += poly[1][i] * r * poly[1][j];
+                den += poly[0][i] * r * poly[0][j];
+            }
+        out[f] = log(num / den);
+    }
+}
+
+// ---- weighted spectral slope (compute_metrics.py:80-274): one block per frame.  Windowed frame / 32768 -> power spectrum of the first
+// nfft / 2 bins by a direct DFT against a shared twiddle table (nfft = 1024: 512 bins x 480 samples per signal) -> 25 critical-band
+// energies in dB (filter matrix supplied by the caller, floor 1e-10) -> slopes, nearest-peak search and Klatt weights by thread 0.
+constexpr int WSS_NB = 25, WSS_MAXFFT = 1024;
+__device__ void wss_peaks(const double* e, const double* sl, double* pk) {
+    for (int i = 0; i < WSS_NB - 1; ++i) {
+        int n = i;
+        if (sl[i] > 0) {
+            while (n < WSS_NB - 1 && sl[n] > 0) ++n;
+            pk[i] = e[n - 1];
+        } else {
+            while (n >= 0 && sl[n] <= 0) --n;
+            pk[i] = e[n + 1];
+        }
+    }
+}
+
+__global__ void wss_kernel(const double* __restrict__ c, const double* __restrict__ p, int W, int skip, int nfft, const double* __restrict__ filt,
+                           double* __restrict__ out, int serial) {
+    extern __shared__ double sm[];
+    double* fc = sm;                     // [W]
+    double* fp = fc + LLR_MAXW;          // [W]
+    double* tw = fp + LLR_MAXW;          // cos, sin tables [nfft] each
+    double* sc = tw + 2 * WSS_MAXFFT;    // power spectra [nfft / 2] each
+    double* sp = sc + WSS_MAXFFT / 2;
+    __shared__ double ec[WSS_NB], ep[WSS_NB];
+    const int f = blockIdx.x, tid = threadIdx.x, half = nfft / 2;
+    const long s0 = (long)f * skip;
+    const double PI = 3.14159265358979323846;
+    for (int i = tid; i < W; i += blockDim.x) {
+        const double w = 0.5 * (1.0 - cos(2.0 * PI * (double)(i + 1) / (double)(W + 1)));
+        fc[i] = c[s0 + i] / 32768.0 * w;
+        fp[i] = p[s0 + i] / 32768.0 * w;
+    }
+    for (int i = tid; i < nfft; i += blockDim.x) {
+        double sn, cs;
+        sincospi(2.0 * (double)i / (double)nfft, &sn, &cs);
+        tw[i] = cs; tw[WSS_MAXFFT + i] = sn;
+    }
+    __syncthreads();
+    for (int k = tid; k < half; k += blockDim.x) {
+        double cr = 0.0, ci = 0.0, pr = 0.0, pi = 0.0;
+        int ph = 0;
+        for (int n = 0; n < W; ++n) {
+            const double cs = tw[ph], sn = tw[WSS_MAXFFT + ph];
+            cr += fc[n] * cs; ci -= fc[n] * sn;
+            pr += fp[n] * cs; pi -= fp[n] * sn;
+            ph += k;
+            if (ph >= nfft) ph -= nfft;
+        }
+        sc[k] = cr * cr + ci * ci;
+        sp[k] = pr * pr + pi * pi;
+    }
+    __syncthreads();
+    if (serial) {
+        if (tid < 2 * WSS_NB) {
+            const int b = tid % WSS_NB;
+            const double* spec = tid < WSS_NB ? sc : sp;
+            double acc = 0.0;
+            for (int j = 0; j < half; ++j) acc += filt[b * half + j] * spec[j];
+            const double v = 10.0 * log10(fmax(acc, 1e-10));
+            if (tid < WSS_NB) ec[b] = v; else ep[b] = v;
+        }
+    } else {
+        for (int job = tid >> 5; job < 2 * WSS_NB; job += blockDim.x >> 5) {
+            const int b = job % WSS_NB, lane = tid & 31;
+            const double* spec = job < WSS_NB ? sc : sp;
+            double acc = 0.0;
+            for (int j = lane; j < half; j += 32) acc += filt[b * half + j] * spec[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const double v = 10.0 * log10(fmax(acc, 1e-10));
+            if (lane == 0) { if (job < WSS_NB) ec[b] = v; else ep[b] = v; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double csl[WSS_NB - 1], psl[WSS_NB - 1], cpk[WSS_NB - 1], ppk[WSS_NB - 1];
+        double cmax = ec[0], pmax = ep[0];
+        for (int i = 0; i < WSS_NB - 1; ++i) { csl[i] = ec[i + 1] - ec[i]; psl[i] = ep[i + 1] - ep[i]; }
+        for (int i = 1; i < WSS_NB; ++i) { cmax = fmax(cmax, ec[i]); pmax = fmax(pmax, ep[i]); }
+        wss_peaks(ec, csl, cpk);
+        wss_peaks(ep, psl, ppk);
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < WSS_NB - 1; ++i) {
+            const double wc = (20.0 / (20.0 + cmax - ec[i])) * (1.0 / (1.0 + cpk[i] - ec[i]));
+            const double wp = (20.0 / (20.0 + pmax - ep[i])) * (1.0 / (1.0 + ppk[i] - ep[i]));
+            const double w = 0.5 * (wc + wp), d = csl[i] - psl[i];
+            num += w * d * d;
+            den += w;
+        }
+        out[f] = num / den;
+    }
+}
+
 }  // namespace
 
 // mean segmental SNR (dB) of `proc` against `clean` (float64, L samples): out[0] must be zero on entry.  nfr = int(L / skip - W / skip) is the
@@ -237,4 +401,32 @@ CMGAN_API int cmgan_stoi_f64(const double* clean, const double* proc, long long 
     band_env_kernel<<<dim3(nframes, 2), 128, 0, st>>>(xs, ys, cnt, band_lo, band_hi, X, Y, nframes);
     if (nframes > NSEG) stoi_segment_kernel<<<nframes - NSEG + 1, 32, 0, st>>>(X, Y, cnt, nframes, out);
     return cmgan_check_launch("stoi kernels");
+}
+
+// per-frame log-likelihood ratios (compute_metrics.py:277-318); nfr = int((L - W) / skip) frames, out[nfr]; the caller sorts / trims (:52-55)
+CMGAN_API int cmgan_llr_f64(const double* clean, const double* proc, long long L, int W, int skip, int order, int nfr, double* out, void* stream) {
+    CMGAN_REQUIRE(clean && proc && out, "cmgan_llr_f64: null pointer");
+    CMGAN_REQUIRE(W > 0 && W <= LLR_MAXW && skip > 0 && order >= 1 && order <= LLR_P && order < W, "cmgan_llr_f64: W=%d order=%d unsupported", W, order);
+    CMGAN_REQUIRE(nfr >= 0 && (long long)(nfr - 1) * skip + W <= L, "cmgan_llr_f64: %d frames do not fit %lld samples", nfr, L);
+    if (nfr == 0) return 0;
+    llr_kernel<<<nfr, 256, 0, (cudaStream_t)stream>>>(clean, proc, W, skip, order, out, getenv("CMGAN_METRICS_SERIAL") != nullptr);
+    return cmgan_check_launch("llr_kernel");
+}
+
+// per-frame weighted-spectral-slope distances (compute_metrics.py:80-274); filt = (25, nfft / 2) critical-band filter matrix, out[nfr]
+CMGAN_API int cmgan_wss_f64(const double* clean, const double* proc, long long L, int W, int skip, int nfft, const double* filt, int nfr,
+                            double* out, void* stream) {
+    CMGAN_REQUIRE(clean && proc && filt && out, "cmgan_wss_f64: null pointer");
+    CMGAN_REQUIRE(W > 0 && W <= LLR_MAXW && skip > 0 && nfft >= W && nfft <= WSS_MAXFFT && (nfft & (nfft - 1)) == 0, "cmgan_wss_f64: W=%d nfft=%d unsupported", W, nfft);
+    CMGAN_REQUIRE(nfr >= 0 && (long long)(nfr - 1) * skip + W <= L, "cmgan_wss_f64: %d frames do not fit %lld samples", nfr, L);
+    if (nfr == 0) return 0;
+    const int smem = (2 * LLR_MAXW + 2 * WSS_MAXFFT + WSS_MAXFFT) * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        CMGAN_REQUIRE(e == cudaSuccess, "cmgan_wss_f64: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    wss_kernel<<<nfr, 256, smem, (cudaStream_t)stream>>>(clean, proc, W, skip, nfft, filt, out, getenv("CMGAN_METRICS_SERIAL") != nullptr);
+    return cmgan_check_launch("wss_kernel");
 }

@@ -106,9 +106,11 @@ int cmgan_mag_bwd_add(const float* er, const float* ei, const float* d_mag, long
 int cmgan_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd, int step, const unsigned long long* step_dev, const float* lr_dev, void* stream);
 int cmgan_counter_add(unsigned long long* p, unsigned long long v, void* stream);
 
-/* ---- PESQ-free scoring on the GPU (src/tools/compute_metrics.py:350-471: segmental SNR, STOI), float64 like the numpy reference */
+/* ---- PESQ-free scoring on the GPU (src/tools/compute_metrics.py: segmental SNR :350-397, STOI :400-471, LLR :277-347, WSS :80-274), float64 like the numpy reference */
 int cmgan_ssnr_f64(const double* clean, const double* proc, long long L, int W, int skip, int nfr, double* out, void* stream);
 long long cmgan_stoi_scratch_doubles(long long L);
+int cmgan_llr_f64(const double* clean, const double* proc, long long L, int W, int skip, int order, int nfr, double* out, void* stream);
+int cmgan_wss_f64(const double* clean, const double* proc, long long L, int W, int skip, int nfft, const double* filt, int nfr, double* out, void* stream);
 int cmgan_stoi_f64(const double* clean, const double* proc, long long L, const double* h, const int* band_lo, const int* band_hi, double* scratch, double* out, void* stream);
 
 /* ---- module level: TSCNet.forward, inference mode (generator.py:160-196; eval BatchNorm, no dropout) as one call.
